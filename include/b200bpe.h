@@ -1,0 +1,105 @@
+/*
+ * b200bpe.h -- C ABI of libb200bpe.so, the B200-native BPE encoder that replaces tiktoken's
+ * Rust extension `_tiktoken` (reference: openai/tiktoken v0.14.0, src/lib.rs + src/py.rs).
+ *
+ * Boundary: this is exactly what a `_tiktoken` replacement binds.  Each entry point names the
+ * reference interface it stands in for (file:line in /root/reference).  Plain pointers and
+ * sizes only; no torch / Python types.  All functions return 0 on success and a negative
+ * B200BPE_E* code on failure; `b200bpe_last_error()` returns a thread-local message.
+ *
+ * There is no CPU fallback: every encode call runs the sm_100a kernels on the device the
+ * engine was created on, and fails with B200BPE_ECUDA if that is not possible.
+ */
+#ifndef B200BPE_H
+#define B200BPE_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200BPE_OK        0
+#define B200BPE_EINVAL   -1   /* bad argument (-> ValueError)                                  */
+#define B200BPE_EPATTERN -2   /* pat_str is not one of the three supported patterns (ValueError;
+                                 the reference raises ValueError for an invalid regex, py.rs:21-22) */
+#define B200BPE_EDUPRANK -3   /* duplicate rank in mergeable_ranks (reference: assert, lib.rs:636-641) */
+#define B200BPE_ECUDA    -4   /* CUDA error / no device (-> RuntimeError)                      */
+#define B200BPE_ENOBYTE  -5   /* a piece needed a single-byte token the vocabulary lacks
+                                 (reference: `ranks[...]` index panic, lib.rs:202,207)         */
+#define B200BPE_EKEY     -6   /* unknown token id in decode (-> KeyError, py.rs:160)           */
+
+typedef struct b200bpe b200bpe_t;
+typedef struct b200bpe_result b200bpe_result_t;
+
+/* CoreBPE::new / py_new (src/lib.rs:601-663, src/py.rs:15-23).
+ * mergeable_ranks is passed flattened: token i has bytes tok_bytes[tok_off[i] .. tok_off[i+1]) and
+ * rank tok_rank[i]; special tokens likewise (UTF-8 strings).  pat_str must be one of the three
+ * pat_strs of tiktoken_ext/openai_public.py (:12-14, :89, :104-114).  Builds the device tables
+ * (rank tables, pair table, Unicode class tables) on CUDA device `device`. */
+int b200bpe_create(const uint8_t *tok_bytes, const uint64_t *tok_off, const uint32_t *tok_rank,
+                   uint32_t n_tok,
+                   const uint8_t *sp_bytes, const uint64_t *sp_off, const uint32_t *sp_rank,
+                   uint32_t n_sp,
+                   const char *pat_str, int device, b200bpe_t **out);
+
+void b200bpe_destroy(b200bpe_t *h);
+
+/* The batched form of CoreBPE::encode_ordinary (src/lib.rs:360-373, py.rs:29-32) as fanned out
+ * by Encoding.encode_ordinary_batch (tiktoken/core.py:164-176): ONE native call for the whole
+ * batch.  text = concatenated UTF-8 of all documents, document d = [doc_off[d], doc_off[d+1]).
+ * HOST buffers; the call copies them to the device, runs the kernels and brings back tokens
+ * (uint32[n_tokens], documents concatenated) and offsets (uint64[n_docs+1]). */
+int b200bpe_encode_ordinary_batch(b200bpe_t *h, const uint8_t *text, const uint64_t *doc_off,
+                                  uint64_t n_docs, b200bpe_result_t **out);
+
+/* The batched form of CoreBPE::encode (src/lib.rs:375-442, py.rs:34-49) as fanned out by
+ * Encoding.encode_batch (core.py:178-206).  allowed[i] != 0 marks special token i (index into
+ * the arrays given to b200bpe_create) as allowed; allowed == NULL means none (then identical to
+ * the ordinary form).  Allowed specials split each document into separate haystacks
+ * (lib.rs:402-405) and are emitted as their own ids (lib.rs:426-436). */
+int b200bpe_encode_batch(b200bpe_t *h, const uint8_t *text, const uint64_t *doc_off, uint64_t n_docs,
+                         const uint8_t *allowed, b200bpe_result_t **out);
+
+/* Device-resident form of the same path, for measurement and for callers that already hold the
+ * corpus in HBM: d_text (n_bytes, readable up to n_bytes+16), d_doc_off (n_docs+1), outputs
+ * d_tokens (capacity n_bytes uint32) and d_tok_off (n_docs+1) are DEVICE pointers on the
+ * engine's device; n_tokens is a host pointer.  `stream` is a cudaStream_t (NULL = engine stream).
+ * The call returns after the stream has been synchronised. */
+int b200bpe_encode_device(b200bpe_t *h, const uint8_t *d_text, uint64_t n_bytes,
+                          const uint64_t *d_doc_off, uint64_t n_docs,
+                          uint32_t *d_tokens, uint64_t *d_tok_off, uint64_t *n_tokens, void *stream);
+
+/* CoreBPE::encode_single_piece (src/py.rs:145-150): BPE of raw bytes without the regex split. */
+int b200bpe_encode_single_piece(b200bpe_t *h, const uint8_t *piece, uint64_t len, b200bpe_result_t **out);
+
+/* Result accessors: the buffers stay valid until b200bpe_result_free (the analogue of
+ * TiktokenBuffer keeping its Vec<Rank> alive, src/py.rs:186-249). */
+const uint32_t *b200bpe_result_tokens(const b200bpe_result_t *r);
+const uint64_t *b200bpe_result_offsets(const b200bpe_result_t *r);
+uint64_t b200bpe_result_n_tokens(const b200bpe_result_t *r);
+uint64_t b200bpe_result_n_docs(const b200bpe_result_t *r);
+void b200bpe_result_free(b200bpe_result_t *r);
+
+/* CoreBPE::decode_bytes (src/lib.rs:345-358, py.rs:156-162): gather of token byte strings.
+ * Host-side table read (not on the encode hot path).  On an unknown id returns B200BPE_EKEY
+ * and stores the id in *bad_token.  out_len receives the byte count; pass out == NULL to size. */
+int b200bpe_decode_bytes(b200bpe_t *h, const uint32_t *tokens, uint64_t n_tokens, uint8_t *out,
+                         uint64_t out_cap, uint64_t *out_len, uint32_t *bad_token);
+
+/* Per-stage device timings (ms, CUDA events on the engine stream) of the most recent encode
+ * call on this handle: [0] mark documents, [1] pre-tokenise, [2] long-piece scan + merge,
+ * [3] encode + compact, [4] total device time, [5] H2D, [6] D2H.  Also kernel launch count. */
+int b200bpe_last_timings(b200bpe_t *h, float *ms7, uint32_t *n_launches);
+
+/* Sizes of the device tables (bytes) for reporting: [0] piece table, [1] pair table,
+ * [2] long-token table + blob, [3] Unicode class tables. */
+int b200bpe_table_bytes(b200bpe_t *h, uint64_t *bytes4);
+
+const char *b200bpe_last_error(void);
+const char *b200bpe_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200BPE_H */

@@ -1,0 +1,239 @@
+"""Drop-in for tiktoken's native module `tiktoken._tiktoken` (reference: src/py.rs).
+
+`CoreBPE(mergeable_ranks, special_tokens, pat_str)` has the constructor and the methods
+`tiktoken/core.py` calls on `self._core_bpe` (core.py:57,76,127,161,259,273,301,358,393),
+plus two batched entry points (`encode_ordinary_batch`, `encode_batch`) that the host class
+uses instead of a thread pool: one native call per batch, executed by hand-written sm_100a
+kernels through the C ABI of libb200bpe.so.  No CPU fallback exists.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import threading
+
+import numpy as np
+
+from . import _lib
+
+
+def _ptr(a: np.ndarray):
+    return C.c_void_p(a.ctypes.data)
+
+
+def _flatten_bytes(items: list[bytes]):
+    blob = b"".join(items)
+    off = np.zeros(len(items) + 1, dtype=np.uint64)
+    if items:
+        np.cumsum(np.fromiter((len(b) for b in items), dtype=np.uint64, count=len(items)), out=off[1:])
+    arr = np.frombuffer(blob, dtype=np.uint8) if blob else np.zeros(1, np.uint8)
+    return arr, off
+
+
+class TokenBuffer:
+    """Owns one native result; exposes tokens / offsets without copying
+    (the role of TiktokenBuffer, src/py.rs:186-249)."""
+
+    def __init__(self, L, handle):
+        self._L, self._h = L, handle
+        self.n_tokens = int(L.b200bpe_result_n_tokens(handle))
+        self.n_docs = int(L.b200bpe_result_n_docs(handle))
+
+    def tokens(self) -> np.ndarray:
+        if self.n_tokens == 0:
+            return np.zeros(0, np.uint32)
+        p = self._L.b200bpe_result_tokens(self._h)
+        a = np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_uint32)), shape=(self.n_tokens,))
+        a.flags.writeable = False
+        return a
+
+    def offsets(self) -> np.ndarray:
+        p = self._L.b200bpe_result_offsets(self._h)
+        a = np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_uint64)), shape=(self.n_docs + 1,))
+        a.flags.writeable = False
+        return a
+
+    def close(self):
+        if self._h:
+            self._L.b200bpe_result_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        self.close()
+
+
+class CoreBPE:
+    def __init__(self, mergeable_ranks: dict[bytes, int], special_tokens: dict[str, int], pat_str: str,
+                 device: int | None = None):
+        L = _lib.lib()
+        self._L = L
+        toks = list(mergeable_ranks.keys())
+        blob, off = _flatten_bytes(toks)
+        ranks = np.fromiter((mergeable_ranks[t] for t in toks), dtype=np.uint32, count=len(toks))
+        self._special_names = list(special_tokens.keys())
+        sblob, soff = _flatten_bytes([s.encode("utf-8") for s in self._special_names])
+        sranks = np.asarray([special_tokens[s] for s in self._special_names], dtype=np.uint32)
+        if len(sranks) == 0:
+            sranks = np.zeros(1, np.uint32)
+        if device is None:
+            import os
+            device = int(os.environ.get("B200BPE_DEVICE", os.environ.get("LOCAL_RANK", "0")))
+        h = C.c_void_p()
+        rc = L.b200bpe_create(_ptr(blob), _ptr(off), _ptr(ranks if len(ranks) else np.zeros(1, np.uint32)),
+                              len(toks), _ptr(sblob), _ptr(soff), _ptr(sranks), len(self._special_names),
+                              pat_str.encode("utf-8"), device, C.byref(h))
+        _lib.check(rc)                      # ValueError for an unsupported pat_str / duplicate ranks
+        self._h = h
+        self.device = device
+        self._encoder = mergeable_ranks
+        self._special = special_tokens
+        self._decoder = None
+        self._lock = threading.Lock()
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h:
+            self._L.b200bpe_destroy(h)
+            self._h = None
+
+    # ---- batched native calls (replace ThreadPoolExecutor fan-out, core.py:164-206) ----------
+    def encode_ordinary_batch_buffer(self, text: np.ndarray, doc_off: np.ndarray) -> TokenBuffer:
+        """text: uint8[N] concatenated UTF-8, doc_off: uint64[n_docs+1] -> TokenBuffer."""
+        res = C.c_void_p()
+        rc = self._L.b200bpe_encode_ordinary_batch(self._h, _ptr(text), _ptr(doc_off), len(doc_off) - 1,
+                                                   C.byref(res))
+        _lib.check(rc)
+        return TokenBuffer(self._L, res)
+
+    def encode_batch_buffer(self, text: np.ndarray, doc_off: np.ndarray, allowed_special) -> TokenBuffer:
+        allowed = np.asarray([1 if s in allowed_special else 0 for s in self._special_names] + [0], np.uint8)
+        res = C.c_void_p()
+        rc = self._L.b200bpe_encode_batch(self._h, _ptr(text), _ptr(doc_off), len(doc_off) - 1, _ptr(allowed),
+                                          C.byref(res))
+        _lib.check(rc)
+        return TokenBuffer(self._L, res)
+
+    @staticmethod
+    def _pack(texts: list[str]):
+        enc = [t.encode("utf-8") for t in texts]      # UnicodeEncodeError on lone surrogates, like &str extraction
+        return _flatten_bytes(enc)
+
+    @staticmethod
+    def _unpack(buf: TokenBuffer) -> list[list[int]]:
+        toks = buf.tokens().tolist()
+        off = buf.offsets().tolist()
+        out = [toks[off[i]:off[i + 1]] for i in range(buf.n_docs)]
+        buf.close()
+        return out
+
+    def encode_ordinary_batch(self, texts: list[str]) -> list[list[int]]:
+        text, off = self._pack(texts)
+        return self._unpack(self.encode_ordinary_batch_buffer(text, off))
+
+    def encode_batch(self, texts: list[str], allowed_special) -> list[list[int]]:
+        text, off = self._pack(texts)
+        return self._unpack(self.encode_batch_buffer(text, off, allowed_special))
+
+    # ---- the per-text methods of src/py.rs -----------------------------------------------------
+    def encode_ordinary(self, text: str) -> list[int]:                      # py.rs:29-32
+        return self.encode_ordinary_batch([text])[0]
+
+    def encode(self, text: str, allowed_special) -> list[int]:              # py.rs:34-49
+        return self.encode_batch([text], allowed_special)[0]
+
+    def encode_to_tiktoken_buffer(self, text: str, allowed_special):        # py.rs:51-70
+        t, off = self._pack([text])
+        buf = self.encode_batch_buffer(t, off, allowed_special)
+        arr = np.array(buf.tokens(), dtype=np.uint32)                      # 1-D 'I' buffer, read-only
+        buf.close()
+        arr.flags.writeable = False
+        return arr
+
+    def encode_single_piece(self, piece: bytes) -> list[int]:               # py.rs:145-150
+        if len(piece) == 0:
+            return []
+        a = np.frombuffer(piece, dtype=np.uint8)
+        res = C.c_void_p()
+        _lib.check(self._L.b200bpe_encode_single_piece(self._h, _ptr(a), len(piece), C.byref(res)))
+        buf = TokenBuffer(self._L, res)
+        out = buf.tokens().tolist()
+        buf.close()
+        return out
+
+    def encode_single_token(self, piece: bytes) -> int:                     # py.rs:133-143 (table read)
+        r = self._encoder.get(bytes(piece))
+        if r is not None:
+            return r
+        try:
+            s = bytes(piece).decode("utf-8")
+        except UnicodeDecodeError:
+            raise KeyError(bytes(piece)) from None
+        if s in self._special:
+            return self._special[s]
+        raise KeyError(bytes(piece))
+
+    def _encode_bytes(self, data: bytes) -> list[int]:                      # py.rs:72-115
+        try:
+            text = data.decode("utf-8")
+        except UnicodeDecodeError:
+            raise NotImplementedError(
+                "_encode_bytes on invalid UTF-8 (unstable-token path, src/py.rs:79-112) is out of scope "
+                "of the B200 encoder") from None
+        return self.encode_ordinary(text)
+
+    def encode_with_unstable(self, text: str, allowed_special):             # py.rs:117-131
+        raise NotImplementedError("encode_with_unstable (completion search, src/lib.rs:444-599) is out of scope")
+
+    def decode_bytes(self, tokens) -> bytes:                                 # py.rs:156-162
+        arr = np.ascontiguousarray(np.asarray(tokens, dtype=np.uint32))
+        n = len(arr)
+        if n == 0:
+            return b""
+        out_len = C.c_uint64(0)
+        bad = C.c_uint32(0)
+        cap = max(64, 8 * n)
+        while True:
+            out = np.empty(cap, np.uint8)
+            rc = self._L.b200bpe_decode_bytes(self._h, _ptr(arr), n, _ptr(out), cap, C.byref(out_len), C.byref(bad))
+            if rc == _lib.EKEY:
+                raise KeyError(f"Invalid token for decoding: {bad.value}")
+            _lib.check(rc)
+            if out_len.value <= cap:
+                return out[:out_len.value].tobytes()
+            cap = int(out_len.value)
+
+    def decode_single_token_bytes(self, token: int) -> bytes:                # py.rs:164-172
+        if self._decoder is None:
+            self._decoder = {v: k for k, v in self._encoder.items()}
+            self._decoder.update({v: k.encode("utf-8") for k, v in self._special.items()})
+        try:
+            return self._decoder[token]
+        except KeyError:
+            raise KeyError(str(token)) from None
+
+    def token_byte_values(self) -> list[bytes]:                              # py.rs:178-183
+        return sorted(self._encoder.keys())
+
+    # ---- measurement hooks ----------------------------------------------------------------------
+    def last_timings(self) -> dict:
+        ms = (C.c_float * 7)()
+        n = C.c_uint32(0)
+        self._L.b200bpe_last_timings(self._h, ms, C.byref(n))
+        keys = ["mark_docs_ms", "pretok_ms", "long_ms", "encode_ms", "device_total_ms", "h2d_ms", "d2h_ms"]
+        d = {k: float(ms[i]) for i, k in enumerate(keys)}
+        d["launches"] = int(n.value)
+        return d
+
+    def table_bytes(self) -> dict:
+        b = (C.c_uint64 * 4)()
+        self._L.b200bpe_table_bytes(self._h, b)
+        return {"piece_table": int(b[0]), "pair_table": int(b[1]), "long_token_table": int(b[2]), "unicode": int(b[3])}
+
+    def encode_device(self, d_text_ptr: int, n_bytes: int, d_doc_off_ptr: int, n_docs: int, d_tokens_ptr: int,
+                      d_tok_off_ptr: int, stream: int = 0) -> int:
+        """Device-resident path (pointers are raw CUDA device addresses); returns n_tokens."""
+        n = C.c_uint64(0)
+        rc = self._L.b200bpe_encode_device(self._h, C.c_void_p(d_text_ptr), n_bytes, C.c_void_p(d_doc_off_ptr),
+                                           n_docs, C.c_void_p(d_tokens_ptr), C.c_void_p(d_tok_off_ptr), C.byref(n),
+                                           C.c_void_p(stream))
+        _lib.check(rc)
+        return int(n.value)

@@ -1,0 +1,995 @@
+// b200bpe.cu -- sm_100a kernels and the C ABI of libb200bpe.so (see include/b200bpe.h).
+//
+// Path replaced: CoreBPE::encode_ordinary / CoreBPE::encode (src/lib.rs:360-442) and the per-call
+// thread pool that fans documents out to it (tiktoken/core.py:164-206).  One call encodes the
+// whole batch:
+//
+//   mark_docs_kernel      doc_off[] -> doc-start bitmask D + first-doc-per-span index
+//   pretok_kernel<PAT>    UTF-8 bytes + D -> piece-start bitmask P   (position-parallel regex rules)
+//   find_long_kernel      P -> queue of pieces longer than 16 bytes (+ scratch offsets)
+//   long_piece_kernel     one warp per long piece: whole-piece probe, then exact round-synchronous
+//                         min-rank merging in HBM/L2 scratch
+//   encode_tiles_kernel   4 KiB tiles: per-piece table probe (1 sector), per-thread merge of the
+//                         misses in shared memory, in-tile compaction, decoupled look-back for the
+//                         global token offset, token + per-document offset write-out
+//
+// No tensor cores: nothing here is a contraction.  The work is byte/integer, bound by HBM reads
+// of the text, L2 probes of the rank tables and instruction issue.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/b200bpe.h"
+#include "bpe_tables.h"
+#include "text_access.cuh"
+#include "unicode_classes.inc"
+
+using namespace b2bpe;
+
+// --------------------------------------------------------------------------------------------
+// error plumbing
+// --------------------------------------------------------------------------------------------
+static thread_local std::string g_last_error;
+static int fail(int code, const std::string &msg) { g_last_error = msg; return code; }
+#define CUDA_TRY(expr)                                                                             \
+    do {                                                                                           \
+        cudaError_t _e = (expr);                                                                   \
+        if (_e != cudaSuccess)                                                                     \
+            return fail(B200BPE_ECUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));        \
+    } while (0)
+
+// --------------------------------------------------------------------------------------------
+// device-side parameter blocks
+// --------------------------------------------------------------------------------------------
+static const int TILE_THREADS = 128;
+static const int TILE_BYTES = TILE_THREADS * 32;     // one 32-byte span (= one bitmask word) per thread
+static const uint32_t ERR_NOBYTE = 1u, ERR_DOCOFF = 2u;
+
+struct UcTables { const uint16_t *stage1; const uint8_t *stage2; const uint8_t *ascii; };
+
+struct Counters {            // device-resident, zeroed per call
+    unsigned long long long_bytes;
+    unsigned int n_long;
+    unsigned int long_head;
+    unsigned int ticket;
+    unsigned int err;
+};
+
+struct LongQ {               // queue of pieces longer than SHORT_MAX bytes
+    unsigned long long *start;   // byte offset of the piece
+    unsigned int *len;
+    unsigned long long *off;     // offset of its region in the long scratch / ltok
+    unsigned int *ntok;
+};
+
+// --------------------------------------------------------------------------------------------
+// kernel 0: documents -> doc-start bitmask, first document index per 32-byte span
+// --------------------------------------------------------------------------------------------
+__global__ void mark_docs_kernel(const unsigned long long *__restrict__ doc_off, unsigned long long n_docs,
+                                 unsigned long long n_bytes, uint32_t *dbits, uint32_t *span_first_doc,
+                                 Counters *ctr) {
+    unsigned long long d = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
+    if (d > n_docs) return;                           // index n_docs is the end sentinel (== n_bytes)
+    unsigned long long pos = doc_off[d];
+    bool bad = pos > n_bytes || (d < n_docs && doc_off[d + 1] < pos) || (d == 0 && pos != 0) ||
+               (d == n_docs && pos != n_bytes);
+    if (bad) { atomicOr(&ctr->err, ERR_DOCOFF); return; }
+    atomicOr(&dbits[pos >> 5], 1u << (pos & 31));
+    atomicMin(&span_first_doc[pos >> 5], (uint32_t)d);
+}
+
+// --------------------------------------------------------------------------------------------
+// kernel 1: pre-tokeniser.  One thread per 32-byte span = one word of the piece-start bitmask.
+// --------------------------------------------------------------------------------------------
+template <int PAT>
+__global__ void __launch_bounds__(256) pretok_kernel(const uint8_t *__restrict__ text, long long n_bytes,
+                                                     const uint32_t *__restrict__ dbits, UcTables uc,
+                                                     uint32_t *__restrict__ pbits, long long n_words) {
+    long long w = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (w >= n_words) return;
+    TextAccess t{text, n_bytes, dbits, uc.stage1, uc.stage2, uc.ascii};
+    const long long base = w * 32;
+    const uint32_t dword = dbits[w];
+    uint32_t word = 0;
+#pragma unroll 1
+    for (int j = 0; j < 32; j++) {
+        long long pos = base + j;
+        if (pos > n_bytes) break;
+        if (pos == n_bytes) { word |= 1u << j; break; }          // end sentinel
+        bool s;
+        if ((dword >> j) & 1u) s = true;
+        else if ((text[pos] & 0xC0u) == 0x80u) s = false;
+        else s = boundary_before<PAT>(t, pos);
+        word |= (uint32_t)s << j;
+    }
+    pbits[w] = word;
+}
+
+// single-piece mode (encode_single_piece): P = {0, n_bytes}
+__global__ void single_piece_bits_kernel(uint32_t *pbits, long long n_bytes, long long n_words) {
+    long long w = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (w >= n_words) return;
+    uint32_t word = 0;
+    if (w == 0) word |= 1u;
+    if ((n_bytes >> 5) == w) word |= 1u << (n_bytes & 31);
+    pbits[w] = word;
+}
+
+// --------------------------------------------------------------------------------------------
+// kernel 2: find pieces longer than SHORT_MAX bytes
+// --------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) find_long_kernel(const uint32_t *__restrict__ pbits, long long n_bytes,
+                                                        long long n_words, LongQ q, uint32_t *lidx,
+                                                        Counters *ctr) {
+    long long w = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (w >= n_words) return;
+    uint32_t m = pbits[w];
+    while (m) {
+        int j = __ffs(m) - 1; m &= m - 1;
+        long long s = w * 32 + j;
+        if (s >= n_bytes) break;
+        long long nxt;
+        if (m) nxt = w * 32 + (__ffs(m) - 1);
+        else {
+            long long w2 = w + 1;
+            uint32_t x = pbits[w2];
+            if (x == 0) {                                       // definitely long: find the end
+                do { w2++; x = pbits[w2]; } while (x == 0);     // the sentinel bit at n_bytes stops this
+            }
+            nxt = w2 * 32 + (__ffs(x) - 1);
+        }
+        long long len = nxt - s;
+        if (len > SHORT_MAX) {
+            unsigned int i = atomicAdd(&ctr->n_long, 1u);
+            unsigned long long off = atomicAdd(&ctr->long_bytes, (unsigned long long)len);
+            q.start[i] = (unsigned long long)s; q.len[i] = (unsigned int)len; q.off[i] = off;
+            lidx[s >> 4] = i;
+        }
+    }
+}
+
+// --------------------------------------------------------------------------------------------
+// kernel 3: long pieces, one warp per piece.
+//
+// Exact parallel form of the reference's merge loop (src/lib.rs:47-138 / :140-196).  A round takes
+// the current global minimum rank g.  Sequentially the reference would merge the g-pairs left to
+// right (ties break leftmost; a merged pair destroys an overlapping g-pair to its right, hence the
+// alternating selection inside a chain of overlapping candidates).  All of them are merged in ONE
+// round, except that the sequential order is only guaranteed while no merge creates a new pair of
+// rank < g; the round therefore commits the selected merges up to and including the first one
+// that does ("violation"), and the next round continues from the exact sequential state.
+// State lives in global scratch (L2 resident): parts as dense arrays id[], rk[] (rank of the pair
+// starting at that part), double buffered for the per-round compaction.
+// --------------------------------------------------------------------------------------------
+struct LongScratch {
+    uint32_t *idA, *rkA, *idB, *rkB, *aux1, *aux2;
+    uint8_t *flag;
+};
+
+__device__ __forceinline__ uint32_t warp_min_u32(uint32_t v) {
+#pragma unroll
+    for (int o = 16; o; o >>= 1) v = min(v, __shfl_xor_sync(0xFFFFFFFFu, v, o));
+    return v;
+}
+
+__device__ uint32_t long_piece_warp(const DevTables &T, const uint8_t *__restrict__ piece, uint32_t n,
+                                    LongScratch S, uint32_t *__restrict__ out, uint32_t *err) {
+    const int lane = threadIdx.x & 31;
+    // whole-piece probe (src/lib.rs:367-368)
+    if (n <= T.max_token_len) {
+        uint32_t r = RANK_MAX;
+        if (lane == 0) {
+            if (n <= (uint32_t)SHORT_MAX) {
+                uint64_t k0 = 0, k1 = 0;
+                for (uint32_t i = 0; i < n; i++) {
+                    if (i < 8) k0 |= (uint64_t)piece[i] << (8 * i); else k1 |= (uint64_t)piece[i] << (8 * (i - 8));
+                }
+                r = piece_lookup16(T, k0, k1, n);
+            } else {
+                uint64_t h = long_hash_init(n);
+                for (uint32_t i = 0; i < n; i += 8) {
+                    uint64_t w = 0;
+                    for (uint32_t k = 0; k < 8 && i + k < n; k++) w |= (uint64_t)piece[i + k] << (8 * k);
+                    h = long_hash_step(h, w);
+                }
+                r = piece_lookup_long(T, h, n, [&](uint32_t i) { return piece[i]; });
+            }
+        }
+        r = __shfl_sync(0xFFFFFFFFu, r, 0);
+        if (r != RANK_MAX) { if (lane == 0) out[0] = r; return 1; }
+    }
+    if (n == 1) {
+        uint32_t id = T.byte_id[piece[0]];
+        if (lane == 0) { out[0] = id; if (id >= PSEUDO_BASE) atomicOr(err, ERR_NOBYTE); }
+        return 1;
+    }
+    uint32_t *id = S.idA, *rk = S.rkA, *id2 = S.idB, *rk2 = S.rkB;
+    for (uint32_t i = lane; i < n; i += 32) {
+        uint32_t b = piece[i];
+        id[i] = __ldg(T.byte_id + b);
+        rk[i] = (i + 1 < n) ? __ldg(T.pair2 + ((b << 8) | piece[i + 1])) : RANK_MAX;
+    }
+    __syncwarp();
+    uint32_t m = n;
+    for (;;) {
+        // A. global minimum rank
+        uint32_t g = RANK_MAX;
+        for (uint32_t i = lane; i < m; i += 32) g = min(g, rk[i]);
+        g = warp_min_u32(g);
+        if (g == RANK_MAX) break;
+        // B. select: odd positions (1st, 3rd, ...) inside each chain of consecutive candidates
+        uint32_t carry_par = 0;                            // parity of the candidate run ending before this tile
+        for (uint32_t base = 0; base < m; base += 32) {
+            uint32_t i = base + lane;
+            bool cand = i < m && rk[i] == g;
+            uint32_t c = __ballot_sync(0xFFFFFFFFu, cand);
+            uint32_t zeros_below = ~c & ((1u << lane) - 1u);
+            uint32_t before;                               // candidates immediately before lane, mod 2
+            if (zeros_below == 0) before = (uint32_t)lane + carry_par;
+            else before = (uint32_t)lane - (32u - (uint32_t)__clz((int)zeros_below));
+            bool sel = cand && ((before & 1u) == 0);
+            if (i < m) S.flag[i] = sel ? 1 : 0;
+            if (c == 0xFFFFFFFFu) carry_par = carry_par;   // 32 more candidates: parity unchanged
+            else carry_par = (uint32_t)__clz((int)~c) & 1u;
+        }
+        __syncwarp();
+        // C. new neighbour ranks of every selected merge, first violation
+        uint32_t vmin = RANK_MAX;
+        for (uint32_t i = lane; i < m; i += 32) {
+            if (!S.flag[i]) continue;
+            uint32_t nl = RANK_MAX, nr = RANK_MAX;
+            if (i >= 1) {
+                uint32_t lid = (i >= 2 && S.flag[i - 2]) ? g : id[i - 1];
+                nl = pair_lookup(T, lid, g);
+            }
+            if (i + 2 < m) nr = pair_lookup(T, g, id[i + 2]);
+            S.aux1[i] = nl; S.aux2[i] = nr;
+            if (nl < g || nr < g) vmin = min(vmin, i);
+        }
+        uint32_t v = warp_min_u32(vmin);
+        __syncwarp();
+        // D. commit merges at positions <= v, compact into the other buffer
+        uint32_t outn = 0;
+        for (uint32_t base = 0; base < m; base += 32) {
+            uint32_t i = base + lane;
+            bool in = i < m;
+            bool com = in && S.flag[i] && i <= v;
+            bool absorbed = in && i >= 1 && S.flag[i - 1] && (i - 1) <= v;
+            bool survive = in && !absorbed;
+            uint32_t sb = __ballot_sync(0xFFFFFFFFu, survive);
+            if (survive) {
+                uint32_t nid, nrk;
+                if (com) {
+                    nid = g;
+                    bool com2 = (i + 2 < m) && S.flag[i + 2] && (i + 2) <= v;
+                    nrk = com2 ? S.aux1[i + 2] : S.aux2[i];
+                } else {
+                    nid = id[i];
+                    bool com1 = (i + 1 < m) && S.flag[i + 1] && (i + 1) <= v;
+                    nrk = com1 ? S.aux1[i + 1] : rk[i];
+                }
+                uint32_t o = outn + __popc(sb & ((1u << lane) - 1u));
+                id2[o] = nid; rk2[o] = nrk;
+            }
+            outn += __popc(sb);
+        }
+        __syncwarp();
+        m = outn;
+        uint32_t *t1 = id; id = id2; id2 = t1;
+        uint32_t *t2 = rk; rk = rk2; rk2 = t2;
+    }
+    bool bad = false;
+    for (uint32_t i = lane; i < m; i += 32) {
+        uint32_t x = id[i];
+        out[i] = x;
+        bad |= x >= PSEUDO_BASE;
+    }
+    if (__any_sync(0xFFFFFFFFu, bad) && lane == 0) atomicOr(err, ERR_NOBYTE);
+    return m;
+}
+
+__global__ void __launch_bounds__(256) long_piece_kernel(const uint8_t *__restrict__ text, DevTables T, LongQ q,
+                                                         LongScratch S, uint32_t *ltok, Counters *ctr) {
+    const int lane = threadIdx.x & 31;
+    const unsigned int n_long = ctr->n_long;
+    for (;;) {
+        unsigned int i = 0;
+        if (lane == 0) i = atomicAdd(&ctr->long_head, 1u);
+        i = __shfl_sync(0xFFFFFFFFu, i, 0);
+        if (i >= n_long) break;
+        unsigned long long off = q.off[i];
+        LongScratch P = S;
+        P.idA += off; P.rkA += off; P.idB += off; P.rkB += off; P.aux1 += off; P.aux2 += off; P.flag += off;
+        uint32_t nt = long_piece_warp(T, text + q.start[i], q.len[i], P, ltok + off, &ctr->err);
+        if (lane == 0) q.ntok[i] = nt;
+        __syncwarp();
+    }
+}
+
+// --------------------------------------------------------------------------------------------
+// kernel 4: tiles.  128 threads x 32 bytes.
+// --------------------------------------------------------------------------------------------
+struct TileParams {
+    const uint8_t *text; long long n_bytes; long long n_words; long long n_tiles;
+    const uint32_t *pbits; const uint32_t *dbits; const uint32_t *span_first_doc;
+    const unsigned long long *doc_off; unsigned long long n_docs;
+    LongQ q; const uint32_t *lidx; const uint32_t *ltok;
+    uint32_t *out; unsigned long long *tok_off;
+    unsigned long long *tile_state; Counters *ctr;
+};
+
+struct SmemCol {                 // per-thread column of a [16][TILE_THREADS] shared array
+    uint32_t *base;
+    __device__ __forceinline__ uint32_t &operator[](int j) const { return base[j * TILE_THREADS]; }
+};
+
+static const unsigned long long ST_AGG = 1ull << 62, ST_INC = 2ull << 62, ST_MASK = (1ull << 62) - 1;
+
+__global__ void __launch_bounds__(TILE_THREADS) encode_tiles_kernel(TileParams p, DevTables T) {
+    __shared__ __align__(16) uint8_t s_text[TILE_BYTES + 32];
+    __shared__ uint32_t s_p[TILE_THREADS + 2];
+    __shared__ uint32_t s_tmask[TILE_THREADS + 1];
+    __shared__ uint32_t s_lmask[TILE_THREADS];
+    __shared__ uint32_t s_tok[TILE_BYTES + SHORT_MAX];
+    __shared__ uint16_t s_miss[TILE_BYTES / 2];
+    __shared__ uint32_t s_id[SHORT_MAX * TILE_THREADS];
+    __shared__ uint32_t s_rk[SHORT_MAX * TILE_THREADS];
+    __shared__ uint32_t s_nmiss, s_tile;
+    __shared__ uint32_t s_warp_tot[TILE_THREADS / 32];
+    __shared__ unsigned long long s_base;
+    __shared__ uint32_t s_ndefer;
+    __shared__ unsigned long long s_defer_dst[TILE_THREADS];
+    __shared__ unsigned long long s_defer_src[TILE_THREADS];
+    __shared__ uint32_t s_defer_n[TILE_THREADS];
+
+    const int tid = threadIdx.x;
+    if (tid == 0) { s_tile = atomicAdd(&p.ctr->ticket, 1u); s_nmiss = 0; s_ndefer = 0; }
+    __syncthreads();
+    const long long tile = s_tile;
+    const long long tile_byte = tile * TILE_BYTES;
+    const long long gw = tile * TILE_THREADS + tid;           // global bitmask word of this thread
+
+    // ---- stage the tile ------------------------------------------------------------------
+    {
+        const long long safe_end = p.n_bytes & ~15ll;          // 16-byte vector loads stay below this
+        for (int v = tid; v < (TILE_BYTES + 32) / 16; v += TILE_THREADS) {
+            long long gpos = tile_byte + (long long)v * 16;
+            uint4 val = make_uint4(0, 0, 0, 0);
+            if (gpos + 16 <= safe_end) val = __ldg(reinterpret_cast<const uint4 *>(p.text + gpos));
+            else if (gpos < p.n_bytes) {
+                uint8_t tmp[16];
+                for (int k = 0; k < 16; k++) tmp[k] = (gpos + k < p.n_bytes) ? p.text[gpos + k] : 0;
+                val = *reinterpret_cast<uint4 *>(tmp);
+            }
+            *reinterpret_cast<uint4 *>(s_text + v * 16) = val;
+        }
+        for (int v = tid; v < TILE_THREADS + 2; v += TILE_THREADS) {
+            long long w = tile * TILE_THREADS + v;
+            s_p[v] = (w < p.n_words) ? p.pbits[w] : 0u;
+        }
+        s_tmask[tid] = 0; s_lmask[tid] = 0;
+        if (tid == 0) s_tmask[TILE_THREADS] = 0;
+    }
+    __syncthreads();
+
+    // ---- phase A: whole-piece probe of every piece that starts in this thread's span -------
+    {
+        uint32_t m = s_p[tid];
+        const uint64_t ahead = ((uint64_t)s_p[tid + 1] << 32) | s_p[tid];
+        uint32_t my_tmask = 0, my_lmask = 0;
+        while (m) {
+            const int j = __ffs(m) - 1; m &= m - 1;
+            const int off = tid * 32 + j;
+            if (tile_byte + off >= p.n_bytes) break;
+            const uint64_t rest = (ahead >> j) >> 1;            // piece starts after this one
+            const uint32_t near = (uint32_t)rest & 0xFFFFu;     // ... within the next 16 bytes
+            if (near == 0) { my_lmask |= 1u << j; continue; }   // longer than 16 bytes: long path
+            const int len = __ffs(near);
+            if (len == 1) {
+                uint32_t id = __ldg(T.byte_id + s_text[off]);
+                if (id >= PSEUDO_BASE) atomicOr(&p.ctr->err, ERR_NOBYTE);
+                s_tok[off] = id; my_tmask |= 1u << j;
+                continue;
+            }
+            // gather up to 16 bytes starting at an arbitrary offset from shared memory
+            const uint32_t *wp = reinterpret_cast<const uint32_t *>(s_text) + (off >> 2);
+            const int sh = (off & 3) * 8;
+            uint32_t w0 = wp[0], w1 = wp[1], w2 = wp[2], w3 = wp[3], w4 = wp[4];
+            uint32_t a0 = __funnelshift_r(w0, w1, sh), a1 = __funnelshift_r(w1, w2, sh);
+            uint32_t a2 = __funnelshift_r(w2, w3, sh), a3 = __funnelshift_r(w3, w4, sh);
+            // zero the bytes beyond len
+            auto keep = [&](int word_idx) -> uint32_t {
+                int nb = len - 4 * word_idx;
+                return nb >= 4 ? 0xFFFFFFFFu : (nb <= 0 ? 0u : ((1u << (8 * nb)) - 1u));
+            };
+            a0 &= keep(0); a1 &= keep(1); a2 &= keep(2); a3 &= keep(3);
+            const uint64_t k0 = ((uint64_t)a1 << 32) | a0, k1 = ((uint64_t)a3 << 32) | a2;
+            const uint32_t r = piece_lookup16(T, k0, k1, (uint32_t)len);
+            if (r != RANK_MAX) { s_tok[off] = r; my_tmask |= 1u << j; }
+            else {
+                uint32_t slot = atomicAdd(&s_nmiss, 1u);
+                s_miss[slot] = (uint16_t)(off | ((len - 1) << 12));
+            }
+        }
+        if (my_tmask) atomicOr(&s_tmask[tid], my_tmask);
+        s_lmask[tid] = my_lmask;
+    }
+    __syncthreads();
+
+    // ---- phase B: per-thread exact merge of the pieces that missed -------------------------
+    {
+        const uint32_t nmiss = s_nmiss;
+        SmemCol idc{s_id + tid}, rkc{s_rk + tid};
+        for (uint32_t i = tid; i < nmiss; i += TILE_THREADS) {
+            const uint32_t e = s_miss[i];
+            const int off = e & 0xFFF, len = (int)(e >> 12) + 1;
+            const uint8_t *pc = s_text + off;
+            uint32_t mask = merge_short(T, [&](int j) { return (uint32_t)pc[j]; }, len, idc, rkc);
+            bool bad = false;
+            for (uint32_t mm = mask; mm;) {
+                int j = __ffs(mm) - 1; mm &= mm - 1;
+                uint32_t id = idc[j];
+                bad |= id >= PSEUDO_BASE;
+                s_tok[off + j] = id;
+            }
+            if (bad) atomicOr(&p.ctr->err, ERR_NOBYTE);
+            // token-start bits (may straddle two words of s_tmask)
+            const int wi = off >> 5, sh = off & 31;
+            atomicOr(&s_tmask[wi], mask << sh);
+            if (sh + len > 32) atomicOr(&s_tmask[wi + 1], mask >> (32 - sh));
+        }
+    }
+    __syncthreads();
+
+    // ---- phase C: count, scan, look-back --------------------------------------------------
+    const uint32_t tm = s_tmask[tid];
+    const uint32_t lm = s_lmask[tid];
+    const uint32_t extra = (tid == TILE_THREADS - 1) ? s_tmask[TILE_THREADS] : 0u;
+    uint32_t cnt = __popc(tm) + __popc(extra);
+    for (uint32_t mm = lm; mm;) {
+        int j = __ffs(mm) - 1; mm &= mm - 1;
+        long long pos = tile_byte + tid * 32 + j;
+        cnt += p.q.ntok[p.lidx[pos >> 4]];
+    }
+    uint32_t incl = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        uint32_t y = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+        if ((tid & 31) >= o) incl += y;
+    }
+    if ((tid & 31) == 31) s_warp_tot[tid >> 5] = incl;
+    __syncthreads();
+    uint32_t warp_base = 0, tile_total = 0;
+#pragma unroll
+    for (int w = 0; w < TILE_THREADS / 32; w++) {
+        uint32_t x = s_warp_tot[w];
+        if (w < (tid >> 5)) warp_base += x;
+        tile_total += x;
+    }
+    const uint32_t excl = warp_base + incl - cnt;
+    if (tid == 0) {
+        unsigned long long base = 0;
+        volatile unsigned long long *st = p.tile_state;
+        if (tile == 0) {
+            st[0] = ST_INC | (unsigned long long)tile_total;
+        } else {
+            st[tile] = ST_AGG | (unsigned long long)tile_total;
+            __threadfence();
+            long long t = tile - 1;
+            for (;;) {
+                unsigned long long v = st[t];
+                if ((v >> 62) == 0) continue;               // predecessor not published yet
+                base += v & ST_MASK;
+                if (v & ST_INC) break;
+                t--;
+            }
+            st[tile] = ST_INC | (base + tile_total);
+        }
+        __threadfence();
+        s_base = base;
+    }
+    __syncthreads();
+
+    // ---- phase D: write tokens and per-document offsets -----------------------------------
+    {
+        unsigned long long k = s_base + excl;
+        const uint32_t dm = (gw < p.n_words) ? p.dbits[gw] : 0u;
+        unsigned long long d = dm ? (unsigned long long)p.span_first_doc[gw] : 0ull;
+        uint32_t walk = tm | lm | dm;
+        while (walk) {
+            const int j = __ffs(walk) - 1; walk &= walk - 1;
+            const int off = tid * 32 + j;
+            const long long pos = tile_byte + off;
+            if ((dm >> j) & 1u) {
+                while (d <= p.n_docs && p.doc_off[d] == (unsigned long long)pos) { p.tok_off[d] = k; d++; }
+            }
+            if ((tm >> j) & 1u) { p.out[k++] = s_tok[off]; }
+            else if ((lm >> j) & 1u) {
+                const uint32_t qi = p.lidx[pos >> 4];
+                const uint32_t nt = p.q.ntok[qi];
+                const unsigned long long src = p.q.off[qi];
+                if (nt <= 64) { for (uint32_t x = 0; x < nt; x++) p.out[k + x] = p.ltok[src + x]; }
+                else {
+                    uint32_t slot = atomicAdd(&s_ndefer, 1u);
+                    s_defer_dst[slot] = k; s_defer_src[slot] = src; s_defer_n[slot] = nt;
+                }
+                k += nt;
+            }
+        }
+        for (uint32_t mm = extra; mm;) {
+            int j = __ffs(mm) - 1; mm &= mm - 1;
+            p.out[k++] = s_tok[TILE_BYTES + j];
+        }
+    }
+    __syncthreads();
+    {
+        const uint32_t nd = s_ndefer;                      // big long pieces: whole block copies
+        for (uint32_t i = 0; i < nd; i++) {
+            const unsigned long long dst = s_defer_dst[i], src = s_defer_src[i];
+            const uint32_t nt = s_defer_n[i];
+            for (uint32_t x = tid; x < nt; x += TILE_THREADS) p.out[dst + x] = p.ltok[src + x];
+        }
+    }
+}
+
+// --------------------------------------------------------------------------------------------
+// host side: engine
+// --------------------------------------------------------------------------------------------
+namespace {
+
+// pat_strs of tiktoken_ext/openai_public.py:12-14, :89, :104-114
+const char *R50K_PAT = R"('(?:[sdmt]|ll|ve|re)| ?\p{L}++| ?\p{N}++| ?[^\s\p{L}\p{N}]++|\s++$|\s+(?!\S)|\s)";
+const char *CL100K_PAT =
+    R"('(?i:[sdmt]|ll|ve|re)|[^\r\n\p{L}\p{N}]?+\p{L}++|\p{N}{1,3}+| ?[^\s\p{L}\p{N}]++[\r\n]*+|\s++$|\s*[\r\n]|\s+(?!\S)|\s)";
+const char *O200K_PAT =
+    R"([^\r\n\p{L}\p{N}]?[\p{Lu}\p{Lt}\p{Lm}\p{Lo}\p{M}]*[\p{Ll}\p{Lm}\p{Lo}\p{M}]+(?i:'s|'t|'re|'ve|'m|'ll|'d)?|)"
+    R"([^\r\n\p{L}\p{N}]?[\p{Lu}\p{Lt}\p{Lm}\p{Lo}\p{M}]+[\p{Ll}\p{Lm}\p{Lo}\p{M}]*(?i:'s|'t|'re|'ve|'m|'ll|'d)?|)"
+    R"(\p{N}{1,3}| ?[^\s\p{L}\p{N}]+[\r\n/]*|\s*[\r\n]+|\s+(?!\S)|\s+)";
+
+template <class Tp>
+struct DevBuf {
+    Tp *p = nullptr; size_t cap = 0;
+    cudaError_t ensure(size_t n) {
+        if (n <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        size_t want = n + n / 8 + 256;
+        cudaError_t e = cudaMalloc((void **)&p, want * sizeof(Tp));
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+struct PinnedBuf {
+    void *p = nullptr; size_t cap = 0;
+};
+
+}  // namespace
+
+struct b200bpe_result {
+    b200bpe *owner = nullptr;
+    PinnedBuf tok, off;                 // pinned when produced by the engine
+    std::vector<uint32_t> vtok;         // used when the result is assembled on the host (specials)
+    std::vector<uint64_t> voff;
+    bool on_host_vec = false;
+    uint64_t n_tokens = 0, n_docs = 0;
+};
+
+struct b200bpe {
+    int device = 0;
+    int pattern = 0;
+    HostTables H;
+    std::vector<std::string> specials; std::vector<uint32_t> special_rank;
+    std::unordered_map<uint32_t, std::string> special_decoder;
+    // device tables
+    uint32_t *d_byte_id = nullptr, *d_pair2 = nullptr;
+    U4 *d_pair_tab = nullptr, *d_piece_tab = nullptr, *d_long_tab = nullptr;
+    uint8_t *d_long_blob = nullptr;
+    uint16_t *d_uc1 = nullptr; uint8_t *d_uc2 = nullptr, *d_ascii = nullptr;
+    DevTables T; UcTables uc;
+    uint64_t table_bytes[4] = {0, 0, 0, 0};
+    // workspace (grow-only)
+    DevBuf<uint8_t> w_text; DevBuf<unsigned long long> w_docoff, w_tokoff, w_tile_state;
+    DevBuf<uint32_t> w_dbits, w_pbits, w_sfd, w_lidx, w_out, w_ltok;
+    DevBuf<unsigned long long> w_lq_start, w_lq_off; DevBuf<unsigned int> w_lq_len, w_lq_ntok;
+    DevBuf<uint32_t> w_idA, w_rkA, w_idB, w_rkB, w_aux1, w_aux2; DevBuf<uint8_t> w_flag;
+    Counters *d_ctr = nullptr; Counters *h_ctr = nullptr;   // h_ctr pinned
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[8];
+    float last_ms[7] = {0, 0, 0, 0, 0, 0, 0};
+    uint32_t last_launches = 0;
+    std::mutex mu;
+    std::vector<PinnedBuf> pinned_pool;
+
+    PinnedBuf take_pinned(size_t bytes) {
+        for (size_t i = 0; i < pinned_pool.size(); i++)
+            if (pinned_pool[i].cap >= bytes) { PinnedBuf b = pinned_pool[i]; pinned_pool.erase(pinned_pool.begin() + i); return b; }
+        PinnedBuf b; size_t want = bytes + bytes / 8 + 4096;
+        if (cudaHostAlloc(&b.p, want, cudaHostAllocDefault) != cudaSuccess) { b.p = nullptr; b.cap = 0; return b; }
+        b.cap = want; return b;
+    }
+    void give_pinned(PinnedBuf b) {
+        if (!b.p) return;
+        if (pinned_pool.size() >= 4) { cudaFreeHost(b.p); return; }
+        pinned_pool.push_back(b);
+    }
+};
+
+template <class Tp>
+static cudaError_t upload(Tp **dst, const void *src, size_t bytes) {
+    cudaError_t e = cudaMalloc((void **)dst, bytes ? bytes : 16);
+    if (e != cudaSuccess) return e;
+    return cudaMemcpy(*dst, src, bytes, cudaMemcpyHostToDevice);
+}
+
+extern "C" const char *b200bpe_last_error(void) { return g_last_error.c_str(); }
+extern "C" const char *b200bpe_version(void) { return "b200bpe 0.1 (sm_100a)"; }
+
+extern "C" int b200bpe_create(const uint8_t *tok_bytes, const uint64_t *tok_off, const uint32_t *tok_rank,
+                              uint32_t n_tok, const uint8_t *sp_bytes, const uint64_t *sp_off,
+                              const uint32_t *sp_rank, uint32_t n_sp, const char *pat_str, int device,
+                              b200bpe_t **out) {
+    if (!out || !pat_str || (n_tok && (!tok_bytes || !tok_off || !tok_rank))) return fail(B200BPE_EINVAL, "null argument");
+    int pattern;
+    if (strcmp(pat_str, R50K_PAT) == 0) pattern = PAT_R50K;
+    else if (strcmp(pat_str, CL100K_PAT) == 0) pattern = PAT_CL100K;
+    else if (strcmp(pat_str, O200K_PAT) == 0) pattern = PAT_O200K;
+    else return fail(B200BPE_EPATTERN,
+                     "unsupported pat_str: the B200 pre-tokeniser implements exactly the r50k/p50k, cl100k and "
+                     "o200k patterns of tiktoken_ext/openai_public.py (there is no CPU regex fallback)");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return fail(B200BPE_ECUDA, "no CUDA device: libb200bpe has no CPU fallback");
+    if (device < 0 || device >= ndev) return fail(B200BPE_EINVAL, "bad device index");
+    b200bpe *h = new b200bpe();
+    h->device = device; h->pattern = pattern;
+    int rc = build_tables(tok_bytes, tok_off, tok_rank, n_tok, h->H);
+    if (rc) { std::string m = h->H.error; delete h; return fail(rc == -3 ? B200BPE_EDUPRANK : B200BPE_EINVAL, m); }
+    for (uint32_t i = 0; i < n_sp; i++) {
+        std::string s((const char *)sp_bytes + sp_off[i], (size_t)(sp_off[i + 1] - sp_off[i]));
+        h->specials.push_back(s); h->special_rank.push_back(sp_rank[i]);
+        h->special_decoder[sp_rank[i]] = s;
+    }
+    cudaError_t e = cudaSetDevice(device);
+    const HostTables &H = h->H;
+    uint8_t ascii[128];
+    for (int i = 0; i < 128; i++) ascii[i] = UC_STAGE2[(uint32_t)UC_STAGE1[0] * 256 + i];
+    if (e == cudaSuccess) e = upload(&h->d_byte_id, H.byte_id.data(), 256 * 4);
+    if (e == cudaSuccess) e = upload(&h->d_pair2, H.pair2.data(), 65536 * 4);
+    if (e == cudaSuccess) e = upload(&h->d_pair_tab, H.pair_tab.data(), H.pair_tab.size() * sizeof(U4));
+    if (e == cudaSuccess) e = upload(&h->d_piece_tab, H.piece_tab.data(), H.piece_tab.size() * sizeof(U4));
+    if (e == cudaSuccess) e = upload(&h->d_long_tab, H.long_tab.data(), H.long_tab.size() * sizeof(U4));
+    if (e == cudaSuccess) e = upload(&h->d_long_blob, H.long_blob.data(), H.long_blob.size());
+    if (e == cudaSuccess) e = upload(&h->d_uc1, UC_STAGE1, sizeof(UC_STAGE1));
+    if (e == cudaSuccess) e = upload(&h->d_uc2, UC_STAGE2, sizeof(UC_STAGE2));
+    if (e == cudaSuccess) e = upload(&h->d_ascii, ascii, 128);
+    if (e == cudaSuccess) e = cudaMalloc((void **)&h->d_ctr, sizeof(Counters));
+    if (e == cudaSuccess) e = cudaHostAlloc((void **)&h->h_ctr, sizeof(Counters), cudaHostAllocDefault);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+    for (int i = 0; i < 8 && e == cudaSuccess; i++) e = cudaEventCreate(&h->ev[i]);
+    if (e != cudaSuccess) { std::string m = cudaGetErrorString(e); delete h; return fail(B200BPE_ECUDA, "table upload: " + m); }
+    h->T.byte_id = h->d_byte_id; h->T.pair2 = h->d_pair2;
+    h->T.pair_tab = h->d_pair_tab; h->T.pair_mask = H.pair_mask;
+    h->T.piece_tab = h->d_piece_tab; h->T.piece_mask = H.piece_mask;
+    h->T.long_tab = h->d_long_tab; h->T.long_mask = H.long_mask;
+    h->T.long_blob = h->d_long_blob; h->T.max_token_len = H.max_token_len; h->T.n_long_tokens = H.n_long_tokens;
+    h->uc.stage1 = h->d_uc1; h->uc.stage2 = h->d_uc2; h->uc.ascii = h->d_ascii;
+    h->table_bytes[0] = H.piece_tab.size() * sizeof(U4);
+    h->table_bytes[1] = H.pair_tab.size() * sizeof(U4) + 65536 * 4 + 1024;
+    h->table_bytes[2] = H.long_tab.size() * sizeof(U4) + H.long_blob.size();
+    h->table_bytes[3] = sizeof(UC_STAGE1) + sizeof(UC_STAGE2) + 128;
+    *out = h;
+    return B200BPE_OK;
+}
+
+extern "C" void b200bpe_destroy(b200bpe_t *h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    cudaFree(h->d_byte_id); cudaFree(h->d_pair2); cudaFree(h->d_pair_tab); cudaFree(h->d_piece_tab);
+    cudaFree(h->d_long_tab); cudaFree(h->d_long_blob); cudaFree(h->d_uc1); cudaFree(h->d_uc2); cudaFree(h->d_ascii);
+    cudaFree(h->d_ctr); if (h->h_ctr) cudaFreeHost(h->h_ctr);
+    h->w_text.release(); h->w_docoff.release(); h->w_tokoff.release(); h->w_tile_state.release();
+    h->w_dbits.release(); h->w_pbits.release(); h->w_sfd.release(); h->w_lidx.release(); h->w_out.release();
+    h->w_ltok.release(); h->w_lq_start.release(); h->w_lq_off.release(); h->w_lq_len.release(); h->w_lq_ntok.release();
+    h->w_idA.release(); h->w_rkA.release(); h->w_idB.release(); h->w_rkB.release(); h->w_aux1.release();
+    h->w_aux2.release(); h->w_flag.release();
+    for (auto &b : h->pinned_pool) cudaFreeHost(b.p);
+    for (int i = 0; i < 8; i++) cudaEventDestroy(h->ev[i]);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+}
+
+// The device pipeline.  All pointers are device pointers on h->device; d_text must be 16-byte
+// aligned.  Caller holds h->mu.  `single_piece`: treat the whole buffer as one piece (no regex).
+static int run_pipeline(b200bpe *h, const uint8_t *d_text, uint64_t n_bytes, const unsigned long long *d_doc_off,
+                        uint64_t n_docs, uint32_t *d_out, unsigned long long *d_tok_off, cudaStream_t st,
+                        bool single_piece) {
+    if (n_bytes >= (1ull << 32) - 4096) return fail(B200BPE_EINVAL, "batch too large for one call (>= 4 GiB)");
+    if (n_docs >= 0xFFFFFFFEull) return fail(B200BPE_EINVAL, "too many documents in one call");
+    const long long n_words = (long long)((n_bytes + 1 + 31) / 32);
+    const long long n_tiles = (n_words + TILE_THREADS - 1) / TILE_THREADS;
+    CUDA_TRY(h->w_dbits.ensure((size_t)n_words + 4));
+    CUDA_TRY(h->w_pbits.ensure((size_t)n_words + 4));
+    CUDA_TRY(h->w_sfd.ensure((size_t)n_words + 4));
+    CUDA_TRY(h->w_tile_state.ensure((size_t)n_tiles + 1));
+    CUDA_TRY(h->w_lidx.ensure((size_t)(n_bytes >> 4) + 4));
+    const size_t qcap = (size_t)(n_bytes / (SHORT_MAX + 1)) + 4;
+    CUDA_TRY(h->w_lq_start.ensure(qcap)); CUDA_TRY(h->w_lq_off.ensure(qcap));
+    CUDA_TRY(h->w_lq_len.ensure(qcap)); CUDA_TRY(h->w_lq_ntok.ensure(qcap));
+    LongQ q{h->w_lq_start.p, h->w_lq_len.p, h->w_lq_off.p, h->w_lq_ntok.p};
+    uint32_t launches = 0;
+
+    CUDA_TRY(cudaEventRecord(h->ev[0], st));
+    CUDA_TRY(cudaMemsetAsync(h->d_ctr, 0, sizeof(Counters), st));
+    CUDA_TRY(cudaMemsetAsync(h->w_dbits.p, 0, ((size_t)n_words + 4) * 4, st));
+    CUDA_TRY(cudaMemsetAsync(h->w_sfd.p, 0xFF, ((size_t)n_words + 4) * 4, st));
+    CUDA_TRY(cudaMemsetAsync(h->w_pbits.p + n_words, 0, 4 * 4, st));
+    CUDA_TRY(cudaMemsetAsync(h->w_tile_state.p, 0, ((size_t)n_tiles + 1) * 8, st));
+    {
+        unsigned long long nd1 = n_docs + 1;
+        mark_docs_kernel<<<(unsigned)((nd1 + 255) / 256), 256, 0, st>>>(d_doc_off, n_docs, n_bytes, h->w_dbits.p,
+                                                                       h->w_sfd.p, h->d_ctr);
+        launches++;
+    }
+    CUDA_TRY(cudaEventRecord(h->ev[1], st));
+    {
+        unsigned grid = (unsigned)((n_words + 255) / 256);
+        if (single_piece) single_piece_bits_kernel<<<grid, 256, 0, st>>>(h->w_pbits.p, (long long)n_bytes, n_words);
+        else if (h->pattern == PAT_R50K)
+            pretok_kernel<PAT_R50K><<<grid, 256, 0, st>>>(d_text, (long long)n_bytes, h->w_dbits.p, h->uc, h->w_pbits.p, n_words);
+        else if (h->pattern == PAT_CL100K)
+            pretok_kernel<PAT_CL100K><<<grid, 256, 0, st>>>(d_text, (long long)n_bytes, h->w_dbits.p, h->uc, h->w_pbits.p, n_words);
+        else
+            pretok_kernel<PAT_O200K><<<grid, 256, 0, st>>>(d_text, (long long)n_bytes, h->w_dbits.p, h->uc, h->w_pbits.p, n_words);
+        launches++;
+    }
+    CUDA_TRY(cudaEventRecord(h->ev[2], st));
+    {
+        unsigned grid = (unsigned)((n_words + 255) / 256);
+        find_long_kernel<<<grid, 256, 0, st>>>(h->w_pbits.p, (long long)n_bytes, n_words, q, h->w_lidx.p, h->d_ctr);
+        launches++;
+    }
+    CUDA_TRY(cudaMemcpyAsync(h->h_ctr, h->d_ctr, sizeof(Counters), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    if (h->h_ctr->err & ERR_DOCOFF) return fail(B200BPE_EINVAL, "document offsets must start at 0, be non-decreasing and end at n_bytes");
+    const unsigned int n_long = h->h_ctr->n_long;
+    const size_t long_bytes = (size_t)h->h_ctr->long_bytes;
+    if (n_long) {
+        CUDA_TRY(h->w_ltok.ensure(long_bytes + 4));
+        CUDA_TRY(h->w_idA.ensure(long_bytes + 4)); CUDA_TRY(h->w_rkA.ensure(long_bytes + 4));
+        CUDA_TRY(h->w_idB.ensure(long_bytes + 4)); CUDA_TRY(h->w_rkB.ensure(long_bytes + 4));
+        CUDA_TRY(h->w_aux1.ensure(long_bytes + 4)); CUDA_TRY(h->w_aux2.ensure(long_bytes + 4));
+        CUDA_TRY(h->w_flag.ensure(long_bytes + 4));
+        LongScratch S{h->w_idA.p, h->w_rkA.p, h->w_idB.p, h->w_rkB.p, h->w_aux1.p, h->w_aux2.p, h->w_flag.p};
+        unsigned warps = n_long;
+        unsigned blocks = (warps + 7) / 8;
+        if (blocks > 148 * 8) blocks = 148 * 8;
+        long_piece_kernel<<<blocks, 256, 0, st>>>(d_text, h->T, q, S, h->w_ltok.p, h->d_ctr);
+        launches++;
+    } else {
+        CUDA_TRY(h->w_ltok.ensure(4));
+    }
+    CUDA_TRY(cudaEventRecord(h->ev[3], st));
+    {
+        TileParams p;
+        p.text = d_text; p.n_bytes = (long long)n_bytes; p.n_words = n_words; p.n_tiles = n_tiles;
+        p.pbits = h->w_pbits.p; p.dbits = h->w_dbits.p; p.span_first_doc = h->w_sfd.p;
+        p.doc_off = d_doc_off; p.n_docs = n_docs; p.q = q; p.lidx = h->w_lidx.p; p.ltok = h->w_ltok.p;
+        p.out = d_out; p.tok_off = d_tok_off; p.tile_state = h->w_tile_state.p; p.ctr = h->d_ctr;
+        encode_tiles_kernel<<<(unsigned)n_tiles, TILE_THREADS, 0, st>>>(p, h->T);
+        launches++;
+    }
+    CUDA_TRY(cudaEventRecord(h->ev[4], st));
+    CUDA_TRY(cudaMemcpyAsync(h->h_ctr, h->d_ctr, sizeof(Counters), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    CUDA_TRY(cudaGetLastError());
+    cudaEventElapsedTime(&h->last_ms[0], h->ev[0], h->ev[1]);
+    cudaEventElapsedTime(&h->last_ms[1], h->ev[1], h->ev[2]);
+    cudaEventElapsedTime(&h->last_ms[2], h->ev[2], h->ev[3]);
+    cudaEventElapsedTime(&h->last_ms[3], h->ev[3], h->ev[4]);
+    cudaEventElapsedTime(&h->last_ms[4], h->ev[0], h->ev[4]);
+    h->last_launches = launches;
+    if (h->h_ctr->err & ERR_NOBYTE)
+        return fail(B200BPE_ENOBYTE, "a piece needs a single-byte token that mergeable_ranks does not contain");
+    return B200BPE_OK;
+}
+
+extern "C" int b200bpe_encode_device(b200bpe_t *h, const uint8_t *d_text, uint64_t n_bytes, const uint64_t *d_doc_off,
+                                     uint64_t n_docs, uint32_t *d_tokens, uint64_t *d_tok_off, uint64_t *n_tokens,
+                                     void *stream) {
+    if (!h || !d_doc_off || !d_tokens || !d_tok_off || (n_bytes && !d_text)) return fail(B200BPE_EINVAL, "null argument");
+    std::lock_guard<std::mutex> lk(h->mu);
+    CUDA_TRY(cudaSetDevice(h->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
+    const uint8_t *txt = d_text;
+    if (((uintptr_t)d_text & 15u) != 0) {                       // vector loads need 16-byte alignment
+        CUDA_TRY(h->w_text.ensure((size_t)n_bytes + 64));
+        CUDA_TRY(cudaMemcpyAsync(h->w_text.p, d_text, n_bytes, cudaMemcpyDeviceToDevice, st));
+        txt = h->w_text.p;
+    }
+    h->last_ms[5] = h->last_ms[6] = 0.f;
+    int rc = run_pipeline(h, txt, n_bytes, (const unsigned long long *)d_doc_off, n_docs, d_tokens,
+                          (unsigned long long *)d_tok_off, st, false);
+    if (rc) return rc;
+    if (n_tokens) {
+        unsigned long long total = 0;
+        CUDA_TRY(cudaMemcpyAsync(&total, (unsigned long long *)d_tok_off + n_docs, 8, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+        *n_tokens = total;
+    }
+    return B200BPE_OK;
+}
+
+// host buffers in, pinned host buffers out
+static int encode_host(b200bpe *h, const uint8_t *text, const uint64_t *doc_off, uint64_t n_docs, bool single_piece,
+                       b200bpe_result **out) {
+    const uint64_t n_bytes = doc_off[n_docs];
+    CUDA_TRY(cudaSetDevice(h->device));
+    cudaStream_t st = h->stream;
+    CUDA_TRY(h->w_text.ensure((size_t)n_bytes + 64));
+    CUDA_TRY(h->w_docoff.ensure((size_t)n_docs + 2));
+    CUDA_TRY(h->w_tokoff.ensure((size_t)n_docs + 2));
+    CUDA_TRY(h->w_out.ensure((size_t)n_bytes + 64));
+    CUDA_TRY(cudaEventRecord(h->ev[5], st));
+    if (n_bytes) CUDA_TRY(cudaMemcpyAsync(h->w_text.p, text, n_bytes, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(h->w_docoff.p, doc_off, (n_docs + 1) * 8, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaEventRecord(h->ev[6], st));
+    int rc = run_pipeline(h, h->w_text.p, n_bytes, h->w_docoff.p, n_docs, h->w_out.p, h->w_tokoff.p, st, single_piece);
+    if (rc) return rc;
+    float h2d = 0; cudaEventElapsedTime(&h2d, h->ev[5], h->ev[6]);
+    b200bpe_result *r = new b200bpe_result();
+    r->owner = h; r->n_docs = n_docs;
+    r->off = h->take_pinned((size_t)(n_docs + 1) * 8);
+    if (!r->off.p) { delete r; return fail(B200BPE_ECUDA, "pinned allocation failed"); }
+    CUDA_TRY(cudaEventRecord(h->ev[5], st));
+    CUDA_TRY(cudaMemcpyAsync(r->off.p, h->w_tokoff.p, (n_docs + 1) * 8, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    r->n_tokens = ((uint64_t *)r->off.p)[n_docs];
+    r->tok = h->take_pinned((size_t)r->n_tokens * 4 + 16);
+    if (!r->tok.p) { h->give_pinned(r->off); delete r; return fail(B200BPE_ECUDA, "pinned allocation failed"); }
+    if (r->n_tokens) CUDA_TRY(cudaMemcpyAsync(r->tok.p, h->w_out.p, r->n_tokens * 4, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaEventRecord(h->ev[6], st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    float d2h = 0; cudaEventElapsedTime(&d2h, h->ev[5], h->ev[6]);
+    h->last_ms[5] = h2d; h->last_ms[6] = d2h;
+    *out = r;
+    return B200BPE_OK;
+}
+
+extern "C" int b200bpe_encode_ordinary_batch(b200bpe_t *h, const uint8_t *text, const uint64_t *doc_off,
+                                             uint64_t n_docs, b200bpe_result_t **out) {
+    if (!h || !doc_off || !out) return fail(B200BPE_EINVAL, "null argument");
+    if (doc_off[n_docs] && !text) return fail(B200BPE_EINVAL, "null text");
+    std::lock_guard<std::mutex> lk(h->mu);
+    return encode_host(h, text, doc_off, n_docs, false, out);
+}
+
+extern "C" int b200bpe_encode_single_piece(b200bpe_t *h, const uint8_t *piece, uint64_t len, b200bpe_result_t **out) {
+    if (!h || !out || (len && !piece)) return fail(B200BPE_EINVAL, "null argument");
+    std::lock_guard<std::mutex> lk(h->mu);
+    uint64_t off[2] = {0, len};
+    return encode_host(h, piece, off, 1, true, out);
+}
+
+// CoreBPE::encode (src/lib.rs:375-442): allowed specials cut each document into haystacks on the
+// host (specials are rare; a device multi-pattern scan is a "next" row), the haystacks are encoded
+// as one batch on the device, and the special ids are spliced in while unpacking.
+extern "C" int b200bpe_encode_batch(b200bpe_t *h, const uint8_t *text, const uint64_t *doc_off, uint64_t n_docs,
+                                    const uint8_t *allowed, b200bpe_result_t **out) {
+    if (!h || !doc_off || !out) return fail(B200BPE_EINVAL, "null argument");
+    bool any = false;
+    if (allowed) for (size_t i = 0; i < h->specials.size(); i++) any |= allowed[i] != 0;
+    if (!any) return b200bpe_encode_ordinary_batch(h, text, doc_off, n_docs, out);
+    std::lock_guard<std::mutex> lk(h->mu);
+    // segment list: pseudo-documents = text between allowed specials; special bytes get
+    // zero-length treatment by being skipped (they are excluded through a compacted copy).
+    std::vector<uint8_t> ctext; ctext.reserve((size_t)doc_off[n_docs]);
+    std::vector<uint64_t> seg_off; seg_off.push_back(0);
+    struct Cut { uint64_t seg_index; uint32_t rank; };           // special emitted after segment seg_index
+    std::vector<Cut> cuts; std::vector<uint64_t> doc_first_seg(n_docs + 1);
+    std::vector<std::pair<std::string, uint32_t>> act;
+    for (size_t i = 0; i < h->specials.size(); i++) if (allowed[i] && !h->specials[i].empty()) act.push_back({h->specials[i], h->special_rank[i]});
+    for (uint64_t d = 0; d < n_docs; d++) {
+        doc_first_seg[d] = seg_off.size() - 1;
+        uint64_t s = doc_off[d], e = doc_off[d + 1], pos = s;
+        while (pos < e) {
+            // leftmost allowed special at or after pos (longest on ties)
+            uint64_t best_pos = e; size_t best = (size_t)-1;
+            for (size_t a = 0; a < act.size(); a++) {
+                const std::string &sp = act[a].first;
+                if (sp.size() > e - pos) continue;
+                const void *f = memmem(text + pos, (size_t)(e - pos), sp.data(), sp.size());
+                if (!f) continue;
+                uint64_t fp = (uint64_t)((const uint8_t *)f - text);
+                if (fp < best_pos || (fp == best_pos && best != (size_t)-1 && sp.size() > act[best].first.size())) { best_pos = fp; best = a; }
+            }
+            ctext.insert(ctext.end(), text + pos, text + best_pos);
+            seg_off.push_back(ctext.size());
+            if (best == (size_t)-1) { pos = e; break; }
+            cuts.push_back({seg_off.size() - 2, act[best].second});
+            pos = best_pos + act[best].first.size();
+            if (pos >= e) { seg_off.push_back(ctext.size()); }    // trailing empty haystack after a final special
+        }
+        if (s == e) seg_off.push_back(ctext.size());
+    }
+    doc_first_seg[n_docs] = seg_off.size() - 1;
+    b200bpe_result *seg = nullptr;
+    uint8_t dummy = 0;
+    int rc = encode_host(h, ctext.empty() ? &dummy : ctext.data(), seg_off.data(), seg_off.size() - 1, false, &seg);
+    if (rc) return rc;
+    const uint32_t *stok = (const uint32_t *)seg->tok.p; const uint64_t *soff = (const uint64_t *)seg->off.p;
+    b200bpe_result *r = new b200bpe_result();
+    r->owner = h; r->on_host_vec = true; r->n_docs = n_docs;
+    r->vtok.reserve((size_t)seg->n_tokens + cuts.size()); r->voff.resize(n_docs + 1);
+    size_t ci = 0;
+    for (uint64_t d = 0; d < n_docs; d++) {
+        r->voff[d] = r->vtok.size();
+        for (uint64_t sgi = doc_first_seg[d]; sgi < doc_first_seg[d + 1]; sgi++) {
+            r->vtok.insert(r->vtok.end(), stok + soff[sgi], stok + soff[sgi + 1]);
+            if (ci < cuts.size() && cuts[ci].seg_index == sgi) { r->vtok.push_back(cuts[ci].rank); ci++; }
+        }
+    }
+    r->voff[n_docs] = r->vtok.size(); r->n_tokens = r->vtok.size();
+    h->give_pinned(seg->tok); h->give_pinned(seg->off); delete seg;
+    *out = r;
+    return B200BPE_OK;
+}
+
+extern "C" const uint32_t *b200bpe_result_tokens(const b200bpe_result_t *r) {
+    return r->on_host_vec ? r->vtok.data() : (const uint32_t *)r->tok.p;
+}
+extern "C" const uint64_t *b200bpe_result_offsets(const b200bpe_result_t *r) {
+    return r->on_host_vec ? r->voff.data() : (const uint64_t *)r->off.p;
+}
+extern "C" uint64_t b200bpe_result_n_tokens(const b200bpe_result_t *r) { return r->n_tokens; }
+extern "C" uint64_t b200bpe_result_n_docs(const b200bpe_result_t *r) { return r->n_docs; }
+extern "C" void b200bpe_result_free(b200bpe_result_t *r) {
+    if (!r) return;
+    if (!r->on_host_vec && r->owner) {
+        std::lock_guard<std::mutex> lk(r->owner->mu);
+        r->owner->give_pinned(r->tok); r->owner->give_pinned(r->off);
+    }
+    delete r;
+}
+
+extern "C" int b200bpe_decode_bytes(b200bpe_t *h, const uint32_t *tokens, uint64_t n_tokens, uint8_t *out,
+                                    uint64_t out_cap, uint64_t *out_len, uint32_t *bad_token) {
+    if (!h || (n_tokens && !tokens) || !out_len) return fail(B200BPE_EINVAL, "null argument");
+    uint64_t k = 0;
+    for (uint64_t i = 0; i < n_tokens; i++) {
+        const std::string *s;
+        auto it = h->H.decoder.find(tokens[i]);
+        if (it != h->H.decoder.end()) s = &it->second;
+        else {
+            auto it2 = h->special_decoder.find(tokens[i]);
+            if (it2 == h->special_decoder.end()) {
+                if (bad_token) *bad_token = tokens[i];
+                return fail(B200BPE_EKEY, "Invalid token for decoding: " + std::to_string(tokens[i]));
+            }
+            s = &it2->second;
+        }
+        if (out && k + s->size() <= out_cap) memcpy(out + k, s->data(), s->size());
+        k += s->size();
+    }
+    *out_len = k;
+    return B200BPE_OK;
+}
+
+extern "C" int b200bpe_last_timings(b200bpe_t *h, float *ms7, uint32_t *n_launches) {
+    if (!h) return fail(B200BPE_EINVAL, "null handle");
+    if (ms7) memcpy(ms7, h->last_ms, sizeof(h->last_ms));
+    if (n_launches) *n_launches = h->last_launches;
+    return B200BPE_OK;
+}
+
+extern "C" int b200bpe_table_bytes(b200bpe_t *h, uint64_t *bytes4) {
+    if (!h || !bytes4) return fail(B200BPE_EINVAL, "null argument");
+    memcpy(bytes4, h->table_bytes, sizeof(h->table_bytes));
+    return B200BPE_OK;
+}

@@ -1,0 +1,177 @@
+// bpe_device.cuh -- table layouts, hashing and the per-thread BPE merge shared by the CUDA kernels
+// (and, through hostcheck.cpp, by the CPU-only unit tests of exactly this code).
+//
+// Reference being replaced: the byte-slice -> rank FxHashMap probes and the min-rank merge loop
+// of src/lib.rs:140-211 (`_byte_pair_merge`, `byte_pair_encode`) and the whole-piece probe of
+// src/lib.rs:367-368.
+//
+// Design (B200-first):
+//  * token id == rank.  A single byte the vocabulary lacks gets a pseudo id PSEUDO_BASE+byte so
+//    that merges through it still work; emitting one is the reference's panic (lib.rs:202,207).
+//  * PIECE table: open-addressed, 32-byte slots keyed by the piece bytes themselves
+//    (<= 16 bytes, two little-endian u64 + length) -> exact compare, one 32 B sector per probe.
+//  * LONG-token table: tokens > 16 bytes, keyed by a 64-bit hash, verified against a byte blob.
+//  * PAIR table: (id(A), id(B)) -> rank(A||B) for every split of every token into two parts that
+//    are themselves tokens (or single bytes).  Because every part produced by the merge loop is
+//    a token, probing bytes(A)||bytes(B) in the reference's map is the same as probing
+//    (id(A), id(B)) here -- fixed 8-byte keys, no variable-length hashing inside the loop
+//    (the reference's own remark, lib.rs:145-147 and :259-260).  16-byte slots.
+//  * PAIR2: direct 64 Ki-entry table for the initial byte pairs (lib.rs:149-155).
+#pragma once
+#include <stdint.h>
+#include "pretok_rules.cuh"
+
+namespace b2bpe {
+
+static const uint32_t RANK_MAX = 0xFFFFFFFFu;
+static const uint32_t PSEUDO_BASE = 0xFFFFFE00u;   // ids >= this are "byte missing from vocabulary"
+static const int SHORT_MAX = 16;                   // pieces up to this length take the per-thread path
+
+struct U4 { uint32_t x, y, z, w; };                // host mirror of uint4
+
+struct DevTables {
+    const uint32_t *byte_id;      // [256]
+    const uint32_t *pair2;        // [65536] rank of the 2-byte token b0,b1 (index b0*256+b1) or RANK_MAX
+    const U4 *pair_tab;           // slots {a, b, rank, 0}; empty: a == 0xFFFFFFFF
+    uint32_t pair_mask;
+    const U4 *piece_tab;          // 2 x U4 per slot: {k0lo,k0hi,k1lo,k1hi} {len, rank, 0, 0}; empty: len == 0
+    uint32_t piece_mask;
+    const U4 *long_tab;           // 2 x U4 per slot: {hlo, hhi, blob_off, len} {rank,0,0,0}; empty: len == 0
+    uint32_t long_mask;
+    const uint8_t *long_blob;
+    uint32_t max_token_len;
+    uint32_t n_long_tokens;
+};
+
+#if defined(__CUDA_ARCH__)
+#define B2_LDG_U4(p) b2bpe::ldg_u4(p)
+#define B2_LDG_U32(p) __ldg(p)
+__device__ __forceinline__ U4 ldg_u4(const U4 *p) {
+    uint4 v = __ldg(reinterpret_cast<const uint4 *>(p));
+    U4 r; r.x = v.x; r.y = v.y; r.z = v.z; r.w = v.w; return r;
+}
+#else
+#define B2_LDG_U4(p) (*(p))
+#define B2_LDG_U32(p) (*(p))
+#endif
+
+B2_HD uint32_t pair_hash(uint32_t a, uint32_t b) {
+    uint32_t h = a * 0x9E3779B1u;
+    h ^= (b + 0x7F4A7C15u) * 0x85EBCA6Bu;
+    h ^= h >> 15; h *= 0x2C1B3C6Du; h ^= h >> 13;
+    return h;
+}
+
+B2_HD uint64_t piece_hash(uint64_t k0, uint64_t k1, uint32_t len) {
+    uint64_t h = (k0 ^ ((uint64_t)len * 0xD6E8FEB86659FD93ull)) * 0x9E3779B97F4A7C15ull;
+    h ^= h >> 32;
+    h = (h ^ k1) * 0xC2B2AE3D27D4EB4Full;
+    h ^= h >> 29;
+    return h;
+}
+
+// 64-bit hash of a byte string given as little-endian u64 words (last one zero padded)
+B2_HD uint64_t long_hash_step(uint64_t h, uint64_t w) {
+    h = (h ^ w) * 0x9E3779B97F4A7C15ull;
+    return h ^ (h >> 32);
+}
+B2_HD uint64_t long_hash_init(uint64_t len) { return len * 0xC2B2AE3D27D4EB4Full + 0x165667B19E3779F9ull; }
+
+B2_HD uint32_t pair_lookup(const DevTables &T, uint32_t a, uint32_t b) {
+    uint32_t s = pair_hash(a, b) & T.pair_mask;
+    for (;;) {
+        U4 e = B2_LDG_U4(T.pair_tab + s);
+        if (e.x == a && e.y == b) return e.z;
+        if (e.x == 0xFFFFFFFFu) return RANK_MAX;
+        s = (s + 1) & T.pair_mask;
+    }
+}
+
+// whole-piece probe for len <= 16 (src/lib.rs:367-368)
+B2_HD uint32_t piece_lookup16(const DevTables &T, uint64_t k0, uint64_t k1, uint32_t len) {
+    uint32_t s = (uint32_t)piece_hash(k0, k1, len) & T.piece_mask;
+    for (;;) {
+        U4 m = B2_LDG_U4(T.piece_tab + 2 * s + 1);
+        if (m.x == 0) return RANK_MAX;
+        if (m.x == len) {
+            U4 k = B2_LDG_U4(T.piece_tab + 2 * s);
+            if (k.x == (uint32_t)k0 && k.y == (uint32_t)(k0 >> 32) && k.z == (uint32_t)k1 && k.w == (uint32_t)(k1 >> 32))
+                return m.y;
+        }
+        s = (s + 1) & T.piece_mask;
+    }
+}
+
+// whole-piece probe for len > 16: hash already computed; bytes compared against the blob
+template <class ByteFn>
+B2_HD uint32_t piece_lookup_long(const DevTables &T, uint64_t h, uint32_t len, ByteFn byte_at) {
+    if (T.n_long_tokens == 0 || len > T.max_token_len) return RANK_MAX;
+    uint32_t s = (uint32_t)(h ^ (h >> 32)) & T.long_mask;
+    for (;;) {
+        U4 k = B2_LDG_U4(T.long_tab + 2 * s);
+        if (k.w == 0) return RANK_MAX;
+        if (k.w == len && k.x == (uint32_t)h && k.y == (uint32_t)(h >> 32)) {
+            const uint8_t *ref = T.long_blob + k.z;
+            bool same = true;
+            for (uint32_t i = 0; i < len; i++) if (ref[i] != byte_at(i)) { same = false; break; }
+            if (same) return B2_LDG_U4(T.long_tab + 2 * s + 1).x;
+        }
+        s = (s + 1) & T.long_mask;
+    }
+}
+
+B2_HD int b2_ffs(uint32_t x) {
+#if defined(__CUDA_ARCH__)
+    return __ffs((int)x);
+#else
+    return __builtin_ffs((int)x);
+#endif
+}
+B2_HD int b2_clz(uint32_t x) {
+#if defined(__CUDA_ARCH__)
+    return __clz((int)x);
+#else
+    return x ? __builtin_clz(x) : 32;
+#endif
+}
+
+// ------------------------------------------------------------------------------------------
+// Per-thread merge for a piece of 2..16 bytes: the literal loop of `_byte_pair_merge`
+// (src/lib.rs:140-196): repeatedly merge the adjacent pair of smallest rank, leftmost on ties
+// (strict `<`, lib.rs:151 / :190), until no adjacent pair is a token.  Parts are a bit mask of
+// start offsets; id[j] / rk[j] hold the part starting at j and the rank of (part j, next part).
+// IdArr / RkArr are per-thread views (a shared-memory column on the device, plain arrays on the
+// host).  Returns the mask of token start offsets; token ids are id[j] at the set bits.
+// ------------------------------------------------------------------------------------------
+template <class ByteFn, class IdArr, class RkArr>
+B2_HD uint32_t merge_short(const DevTables &T, ByteFn byte_at, int n, IdArr id, RkArr rk) {
+    uint32_t prevb = byte_at(0);
+    for (int j = 0; j < n; j++) {
+        uint32_t nb = (j + 1 < n) ? byte_at(j + 1) : 0;
+        id[j] = B2_LDG_U32(T.byte_id + prevb);
+        rk[j] = (j + 1 < n) ? B2_LDG_U32(T.pair2 + (prevb << 8 | nb)) : RANK_MAX;
+        prevb = nb;
+    }
+    uint32_t mask = (n >= 32) ? 0xFFFFFFFFu : ((1u << n) - 1u);
+    for (;;) {
+        uint32_t best = RANK_MAX; int bj = -1;
+        for (uint32_t m = mask; m;) {
+            int j = b2_ffs(m) - 1; m &= m - 1;
+            uint32_t r = rk[j];
+            if (r < best) { best = r; bj = j; }
+        }
+        if (best == RANK_MAX) break;
+        uint32_t above = mask & ~((2u << bj) - 1u);
+        int j2 = b2_ffs(above) - 1;                 // right part of the merged pair
+        mask &= ~(1u << j2);
+        id[bj] = best;                              // id == rank of the merged token
+        above &= ~(1u << j2);
+        if (above) rk[bj] = pair_lookup(T, best, id[b2_ffs(above) - 1]);
+        else rk[bj] = RANK_MAX;
+        uint32_t below = mask & ((1u << bj) - 1u);
+        if (below) { int jp = 31 - b2_clz(below); rk[jp] = pair_lookup(T, id[jp], best); }
+    }
+    return mask;
+}
+
+}  // namespace b2bpe

@@ -8,7 +8,7 @@
 #include "text_access.cuh"
 #include "unicode_classes.inc"
 
-using namespace b200bpe;
+using namespace b2bpe;
 
 extern "C" int hc_piece_starts(int pattern, const uint8_t *text, int64_t n, const uint64_t *doc_off,
                                int64_t n_docs, uint8_t *is_start /* n bytes, 0/1 */) {
@@ -35,4 +35,44 @@ extern "C" int hc_piece_starts(int pattern, const uint8_t *text, int64_t n, cons
         is_start[pos] = s ? 1 : 0;
     }
     return 0;
+}
+
+// ---- table build + per-thread short-piece path (piece probe, merge_short) --------------------
+#include "bpe_tables.h"
+
+struct HcTables { HostTables H; };
+
+extern "C" void *hc_tables_new(const uint8_t *tok_bytes, const uint64_t *tok_off, const uint32_t *tok_rank,
+                               uint32_t n, int *rc) {
+    HcTables *h = new HcTables();
+    *rc = build_tables(tok_bytes, tok_off, tok_rank, n, h->H);
+    if (*rc) { delete h; return nullptr; }
+    return h;
+}
+extern "C" void hc_tables_free(void *p) { delete (HcTables *)p; }
+extern "C" uint64_t hc_tables_pairs(void *p) { return ((HcTables *)p)->H.n_pairs; }
+
+// the short path of the encode kernel for one piece of 1..16 bytes: whole-piece probe
+// (lib.rs:367-368) then merge_short; ids >= PSEUDO_BASE are reported as RANK_MAX.
+extern "C" int hc_encode_short(void *p, const uint8_t *piece, uint32_t len, uint32_t *out) {
+    const HostTables &H = ((HcTables *)p)->H;
+    DevTables T = H.view();
+    if (len == 0 || len > (uint32_t)SHORT_MAX) return -1;
+    uint64_t k0, k1; pack16(piece, len, k0, k1);
+    uint32_t r = piece_lookup16(T, k0, k1, len);
+    if (r != RANK_MAX) { out[0] = r; return 1; }
+    if (len == 1) { uint32_t id = T.byte_id[piece[0]]; out[0] = id >= PSEUDO_BASE ? RANK_MAX : id; return 1; }
+    uint32_t id[32], rk[32];
+    uint32_t mask = merge_short(T, [&](int j) { return (uint32_t)piece[j]; }, (int)len, id, rk);
+    int k = 0;
+    for (uint32_t m = mask; m;) { int j = __builtin_ffs(m) - 1; m &= m - 1; out[k++] = id[j] >= PSEUDO_BASE ? RANK_MAX : id[j]; }
+    return k;
+}
+
+// whole-piece probe for a long piece (> 16 bytes) through the hash + blob verification
+extern "C" uint32_t hc_probe_long(void *p, const uint8_t *piece, uint32_t len) {
+    const HostTables &H = ((HcTables *)p)->H;
+    DevTables T = H.view();
+    uint64_t h = long_hash_bytes(piece, len);
+    return piece_lookup_long(T, h, len, [&](uint32_t i) { return piece[i]; });
 }

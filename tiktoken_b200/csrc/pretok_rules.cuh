@@ -31,7 +31,7 @@
 #define B2_HDN inline
 #endif
 
-namespace b200bpe {
+namespace b2bpe {
 
 enum : int {
     C_O = 0, C_LU = 1, C_LL = 2, C_LB = 3, C_M = 4, C_N = 5, C_SP = 6, C_WS = 7, C_NL = 8,
@@ -374,4 +374,4 @@ B2_HD bool boundary_before(const T &t, int64_t pos) {
     return boundary_o200k(t, pos);
 }
 
-}  // namespace b200bpe
+}  // namespace b2bpe

@@ -5,7 +5,7 @@
 #pragma once
 #include "pretok_rules.cuh"
 
-namespace b200bpe {
+namespace b2bpe {
 
 struct TextAccess {
     const uint8_t *text;
@@ -41,4 +41,4 @@ struct TextAccess {
     }
 };
 
-}  // namespace b200bpe
+}  // namespace b2bpe
