@@ -1,0 +1,96 @@
+"""CPU-only check of the EXACT rule code the pre-tokeniser kernel executes
+(tiktoken_b200/csrc/pretok_rules.cuh, compiled for the host by hostcheck.cpp) against the literal
+backtracking matcher of the oracle."""
+import itertools
+import json
+import os
+import random
+
+import numpy as np
+import pytest
+
+import vocab_util as vu
+from oracle import Oracle
+
+G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+BYTES = {bytes([i]): i for i in range(256)}
+PATS = {"r50k": (0, vu.R50K_PAT), "cl100k": (1, vu.CL100K_PAT), "o200k": (2, vu.O200K_PAT)}
+
+
+def rule_starts(H, pid, docs):
+    blob = b"".join(docs)
+    n = len(blob)
+    off = np.zeros(len(docs) + 1, np.uint64)
+    off[1:] = np.cumsum([len(d) for d in docs])
+    a = np.frombuffer(blob, np.uint8) if n else np.zeros(1, np.uint8)
+    out = np.zeros(n + 1, np.uint8)
+    assert H.hc_piece_starts(pid, a.ctypes.data, n, off.ctypes.data, len(docs), out.ctypes.data) == 0
+    return out[:n], off
+
+
+def expected_starts(o, doc):
+    exp = np.zeros(len(doc), np.uint8)
+    p = 0
+    for piece in o.split(doc):
+        exp[p] = 1
+        p += len(piece)
+    return exp
+
+
+@pytest.mark.parametrize("name", ["r50k", "cl100k", "o200k"])
+def test_rules_exhaustive(hostcheck, name):
+    pid, pat = PATS[name]
+    spec = json.load(open(os.path.join(G, "splits_exhaustive.json")))[name]
+    o = Oracle(BYTES, {}, pat)
+    L = spec["max_len"] - 1                     # one shorter than the oracle pin keeps the CPU suite quick
+    for l in range(1, L + 1):
+        docs = ["".join(t).encode() for t in itertools.product(spec["alphabet"], repeat=l)]
+        got, off = rule_starts(hostcheck, pid, docs)
+        for i, d in enumerate(docs):
+            assert np.array_equal(got[int(off[i]):int(off[i + 1])], expected_starts(o, d)), (name, d)
+
+
+@pytest.mark.parametrize("name", ["r50k", "cl100k", "o200k"])
+def test_rules_random_long_strings(hostcheck, name):
+    """Longer strings over the class alphabet (sampled), incl. long homogeneous runs."""
+    pid, pat = PATS[name]
+    alph = json.load(open(os.path.join(G, "splits_exhaustive.json")))[name]["alphabet"]
+    o = Oracle(BYTES, {}, pat)
+    rnd = random.Random(11)
+    docs = []
+    for _ in range(4000):
+        n = rnd.choice([7, 8, 9, 12, 20, 40])
+        chars = []
+        while len(chars) < n:
+            chars += [rnd.choice(alph)] * rnd.choice([1, 1, 1, 2, 3, 5, 9])
+        docs.append("".join(chars[:n]).encode())
+    got, off = rule_starts(hostcheck, pid, docs)
+    for i, d in enumerate(docs):
+        assert np.array_equal(got[int(off[i]):int(off[i + 1])], expected_starts(o, d)), (name, d)
+
+
+@pytest.mark.parametrize("name", ["r50k", "cl100k", "o200k"])
+def test_rules_on_reference_unicode_cases(hostcheck, name):
+    """The random Unicode strings whose splits come straight from the reference engine; all packed
+    into ONE buffer as separate documents, so document-boundary handling is exercised too."""
+    pid, _ = PATS[name]
+    cases = json.load(open(os.path.join(G, "splits_random.json")))[name]
+    docs = [bytes.fromhex(t) for t, _ in cases]
+    got, off = rule_starts(hostcheck, pid, docs)
+    for i, (t, pieces) in enumerate(cases):
+        exp = np.zeros(len(docs[i]), np.uint8)
+        p = 0
+        for ph in pieces:
+            exp[p] = 1
+            p += len(ph) // 2
+        assert np.array_equal(got[int(off[i]):int(off[i + 1])], exp), docs[i]
+
+
+def test_documents_are_separate_haystacks(hostcheck):
+    # two docs "a  " + "b": the spaces end doc 0, so they stay one piece; as one doc they split
+    got, _ = rule_starts(hostcheck, 1, [b"a  ", b"b"])
+    assert got.tolist() == [1, 1, 0, 1]
+    got, _ = rule_starts(hostcheck, 1, [b"a  b"])
+    assert got.tolist() == [1, 1, 1, 0]
+    got, _ = rule_starts(hostcheck, 1, [b"", b"", b"x", b""])
+    assert got.tolist() == [1]
