@@ -260,7 +260,7 @@ def main():
     barrier()
     sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    stage = {"pretok_ms": [], "encode_ms": [], "long_ms": [], "mark_docs_ms": [], "device_total_ms": []}
+    stage = {"pretok_ms": [], "encode_ms": [], "gather_ms": [], "long_ms": [], "mark_docs_ms": [], "device_total_ms": []}
     launches = 0
     ev0.record(stream)
     for _ in range(args.steps):

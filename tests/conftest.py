@@ -17,7 +17,7 @@ def pytest_configure(config):
 def _build_hostcheck() -> str:
     csrc = os.path.join(ROOT, "tiktoken_b200", "csrc")
     so = os.path.join(csrc, "libb200bpe_hostcheck.so")
-    srcs = [os.path.join(csrc, f) for f in ("hostcheck.cpp", "pretok_rules.cuh", "text_access.cuh", "bpe_device.cuh",
+    srcs = [os.path.join(csrc, f) for f in ("hostcheck.cpp", "pretok_rules.cuh", "pretok_fast.cuh", "text_access.cuh", "bpe_device.cuh",
                                             "bpe_tables.h", "unicode_classes.inc")]
     if not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
         subprocess.check_call(["g++", "-O2", "-fPIC", "-shared", "-std=c++17", "-o", so, srcs[0]])

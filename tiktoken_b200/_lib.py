@@ -14,7 +14,7 @@ import subprocess
 
 _CSRC = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc")
 _SO = os.path.join(_CSRC, "libb200bpe.so")
-_SOURCES = ["b200bpe.cu", "bpe_device.cuh", "bpe_tables.h", "pretok_rules.cuh", "text_access.cuh",
+_SOURCES = ["b200bpe.cu", "bpe_device.cuh", "bpe_tables.h", "pretok_rules.cuh", "pretok_fast.cuh", "text_access.cuh",
             "unicode_classes.inc"]
 
 OK, EINVAL, EPATTERN, EDUPRANK, ECUDA, ENOBYTE, EKEY = 0, -1, -2, -3, -4, -5, -6

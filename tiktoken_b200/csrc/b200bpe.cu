@@ -27,6 +27,7 @@
 #include "../../include/b200bpe.h"
 #include "bpe_tables.h"
 #include "text_access.cuh"
+#include "pretok_fast.cuh"
 #include "unicode_classes.inc"
 
 using namespace b2bpe;
@@ -46,8 +47,6 @@ static int fail(int code, const std::string &msg) { g_last_error = msg; return c
 // --------------------------------------------------------------------------------------------
 // device-side parameter blocks
 // --------------------------------------------------------------------------------------------
-static const int TILE_THREADS = 128;
-static const int TILE_BYTES = TILE_THREADS * 32;     // one 32-byte span (= one bitmask word) per thread
 static const uint32_t ERR_NOBYTE = 1u, ERR_DOCOFF = 2u;
 
 struct UcTables { const uint16_t *stage1; const uint8_t *stage2; const uint8_t *ascii; };
@@ -93,21 +92,7 @@ __global__ void __launch_bounds__(256) pretok_kernel(const uint8_t *__restrict__
     long long w = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (w >= n_words) return;
     TextAccess t{text, n_bytes, dbits, uc.stage1, uc.stage2, uc.ascii};
-    const long long base = w * 32;
-    const uint32_t dword = dbits[w];
-    uint32_t word = 0;
-#pragma unroll 1
-    for (int j = 0; j < 32; j++) {
-        long long pos = base + j;
-        if (pos > n_bytes) break;
-        if (pos == n_bytes) { word |= 1u << j; break; }          // end sentinel
-        bool s;
-        if ((dword >> j) & 1u) s = true;
-        else if ((text[pos] & 0xC0u) == 0x80u) s = false;
-        else s = boundary_before<PAT>(t, pos);
-        word |= (uint32_t)s << j;
-    }
-    pbits[w] = word;
+    pbits[w] = span_boundaries<PAT>(t, w);            // pretok_fast.cuh (+ pretok_rules.cuh for the rare cases)
 }
 
 // single-piece mode (encode_single_piece): P = {0, n_bytes}
@@ -312,228 +297,263 @@ __global__ void __launch_bounds__(256) long_piece_kernel(const uint8_t *__restri
 }
 
 // --------------------------------------------------------------------------------------------
-// kernel 4: tiles.  128 threads x 32 bytes.
+// kernel 4: encode.  One WARP per 1 KiB sub-tile (32 lanes x 32-byte spans), no block barriers:
+// a warp that is waiting on L2 probes or merging its misses never stalls its neighbours.
+// The warp leaves its tokens compacted in a fixed-stride scratch region plus (count, flags);
+// a scan over the counts and a gather kernel (kernel 6) place them -- kernel boundaries do the
+// ordering, there is no look-back chain and no ticket counter.
 // --------------------------------------------------------------------------------------------
 struct TileParams {
-    const uint8_t *text; long long n_bytes; long long n_words; long long n_tiles;
+    const uint8_t *text; long long n_bytes; long long n_words; long long n_sub;
     const uint32_t *pbits; const uint32_t *dbits; const uint32_t *span_first_doc;
     const unsigned long long *doc_off; unsigned long long n_docs;
     LongQ q; const uint32_t *lidx; const uint32_t *ltok;
+    uint32_t *scratch;            // [n_sub][SUB_CAP] short-piece tokens of each sub-tile, compacted in byte order
+    uint32_t *tbits;              // token-start bitmask words (short pieces), one per span
+    uint32_t *sub_count;          // [n_sub] tokens emitted by the sub-tile (short + long)
+    uint32_t *sub_flags;          // [n_sub] bit0: has long piece, bit1: has document start, bits 8..: straddling tokens
+    unsigned long long *sub_base; // [n_sub+1] exclusive prefix of sub_count (kernel 5)
     uint32_t *out; unsigned long long *tok_off;
-    unsigned long long *tile_state; Counters *ctr;
+    Counters *ctr;
 };
 
-struct SmemCol {                 // per-thread column of a [16][TILE_THREADS] shared array
-    uint32_t *base;
-    __device__ __forceinline__ uint32_t &operator[](int j) const { return base[j * TILE_THREADS]; }
+static const int ENC_WARPS = 4;                          // warps per block
+static const int SUB_BYTES = 1024;                       // bytes per warp sub-tile
+static const int SUB_CAP = SUB_BYTES + SHORT_MAX;        // scratch slots per sub-tile (tokens <= bytes)
+
+struct WarpSmem {
+    __align__(16) uint8_t text[SUB_BYTES + 32];
+    uint32_t p[34];
+    uint32_t tmask[33];
+    uint32_t nmiss;
+    uint32_t tok[SUB_BYTES + SHORT_MAX];
+    uint16_t miss[SUB_BYTES / 2];
 };
 
-static const unsigned long long ST_AGG = 1ull << 62, ST_INC = 2ull << 62, ST_MASK = (1ull << 62) - 1;
+__global__ void __launch_bounds__(ENC_WARPS * 32) encode_tiles_kernel(TileParams p, DevTables T) {
+    __shared__ WarpSmem smem[ENC_WARPS];
+    WarpSmem &S = smem[threadIdx.x >> 5];
+    const int lane = threadIdx.x & 31;
+    const long long safe_end = p.n_bytes & ~15ll;
+    const long long sub = (long long)blockIdx.x * ENC_WARPS + (threadIdx.x >> 5);
+    if (sub >= p.n_sub) return;
+    const long long sub_byte = sub * SUB_BYTES;
+    const long long gw = sub * 32 + lane;              // this lane's bitmask word
 
-__global__ void __launch_bounds__(TILE_THREADS) encode_tiles_kernel(TileParams p, DevTables T) {
-    __shared__ __align__(16) uint8_t s_text[TILE_BYTES + 32];
-    __shared__ uint32_t s_p[TILE_THREADS + 2];
-    __shared__ uint32_t s_tmask[TILE_THREADS + 1];
-    __shared__ uint32_t s_lmask[TILE_THREADS];
-    __shared__ uint32_t s_tok[TILE_BYTES + SHORT_MAX];
-    __shared__ uint16_t s_miss[TILE_BYTES / 2];
-    __shared__ uint32_t s_id[SHORT_MAX * TILE_THREADS];
-    __shared__ uint32_t s_rk[SHORT_MAX * TILE_THREADS];
-    __shared__ uint32_t s_nmiss, s_tile;
-    __shared__ uint32_t s_warp_tot[TILE_THREADS / 32];
-    __shared__ unsigned long long s_base;
-    __shared__ uint32_t s_ndefer;
-    __shared__ unsigned long long s_defer_dst[TILE_THREADS];
-    __shared__ unsigned long long s_defer_src[TILE_THREADS];
-    __shared__ uint32_t s_defer_n[TILE_THREADS];
-
-    const int tid = threadIdx.x;
-    if (tid == 0) { s_tile = atomicAdd(&p.ctr->ticket, 1u); s_nmiss = 0; s_ndefer = 0; }
-    __syncthreads();
-    const long long tile = s_tile;
-    const long long tile_byte = tile * TILE_BYTES;
-    const long long gw = tile * TILE_THREADS + tid;           // global bitmask word of this thread
-
-    // ---- stage the tile ------------------------------------------------------------------
-    {
-        const long long safe_end = p.n_bytes & ~15ll;          // 16-byte vector loads stay below this
-        for (int v = tid; v < (TILE_BYTES + 32) / 16; v += TILE_THREADS) {
-            long long gpos = tile_byte + (long long)v * 16;
-            uint4 val = make_uint4(0, 0, 0, 0);
-            if (gpos + 16 <= safe_end) val = __ldg(reinterpret_cast<const uint4 *>(p.text + gpos));
-            else if (gpos < p.n_bytes) {
-                uint8_t tmp[16];
-                for (int k = 0; k < 16; k++) tmp[k] = (gpos + k < p.n_bytes) ? p.text[gpos + k] : 0;
-                val = *reinterpret_cast<uint4 *>(tmp);
-            }
-            *reinterpret_cast<uint4 *>(s_text + v * 16) = val;
+    // ---- stage text (1 KiB + 32 B tail) and piece-start words ----------------------------
+    for (int v = lane; v < (SUB_BYTES + 32) / 16; v += 32) {
+        long long gpos = sub_byte + (long long)v * 16;
+        uint4 val = make_uint4(0, 0, 0, 0);
+        if (gpos + 16 <= safe_end) val = __ldg(reinterpret_cast<const uint4 *>(p.text + gpos));
+        else if (gpos < p.n_bytes) {
+            uint32_t tmp[4] = {0, 0, 0, 0};
+            for (int k = 0; k < 16; k++)
+                if (gpos + k < p.n_bytes) tmp[k >> 2] |= (uint32_t)p.text[gpos + k] << (8 * (k & 3));
+            val = make_uint4(tmp[0], tmp[1], tmp[2], tmp[3]);
         }
-        for (int v = tid; v < TILE_THREADS + 2; v += TILE_THREADS) {
-            long long w = tile * TILE_THREADS + v;
-            s_p[v] = (w < p.n_words) ? p.pbits[w] : 0u;
-        }
-        s_tmask[tid] = 0; s_lmask[tid] = 0;
-        if (tid == 0) s_tmask[TILE_THREADS] = 0;
+        *reinterpret_cast<uint4 *>(S.text + v * 16) = val;
     }
-    __syncthreads();
-
-    // ---- phase A: whole-piece probe of every piece that starts in this thread's span -------
     {
-        uint32_t m = s_p[tid];
-        const uint64_t ahead = ((uint64_t)s_p[tid + 1] << 32) | s_p[tid];
-        uint32_t my_tmask = 0, my_lmask = 0;
+        S.p[lane] = (gw < p.n_words) ? __ldg(p.pbits + gw) : 0u;
+        if (lane < 2) { long long w2 = sub * 32 + 32 + lane; S.p[32 + lane] = (w2 < p.n_words) ? __ldg(p.pbits + w2) : 0u; }
+        S.tmask[lane] = 0;
+        if (lane == 0) { S.tmask[32] = 0; S.nmiss = 0; }
+    }
+    __syncwarp();
+
+    // ---- phase A: whole-piece probe of every piece that starts in this lane's span --------
+    uint32_t lm = 0;                                   // long-piece starts in this span
+    {
+        uint32_t m = S.p[lane];
+        const uint64_t ahead = ((uint64_t)S.p[lane + 1] << 32) | m;
+        uint32_t my_tmask = 0;
         while (m) {
             const int j = __ffs(m) - 1; m &= m - 1;
-            const int off = tid * 32 + j;
-            if (tile_byte + off >= p.n_bytes) break;
-            const uint64_t rest = (ahead >> j) >> 1;            // piece starts after this one
-            const uint32_t near = (uint32_t)rest & 0xFFFFu;     // ... within the next 16 bytes
-            if (near == 0) { my_lmask |= 1u << j; continue; }   // longer than 16 bytes: long path
+            const int off = lane * 32 + j;
+            if (sub_byte + off >= p.n_bytes) break;
+            const uint32_t near = (uint32_t)((ahead >> j) >> 1) & 0xFFFFu;   // piece starts in the next 16 bytes
+            if (near == 0) { lm |= 1u << j; continue; }                       // > 16 bytes: long path
             const int len = __ffs(near);
             if (len == 1) {
-                uint32_t id = __ldg(T.byte_id + s_text[off]);
+                uint32_t id = __ldg(T.byte_id + S.text[off]);
                 if (id >= PSEUDO_BASE) atomicOr(&p.ctr->err, ERR_NOBYTE);
-                s_tok[off] = id; my_tmask |= 1u << j;
+                S.tok[off] = id; my_tmask |= 1u << j;
                 continue;
             }
-            // gather up to 16 bytes starting at an arbitrary offset from shared memory
-            const uint32_t *wp = reinterpret_cast<const uint32_t *>(s_text) + (off >> 2);
+            const uint32_t *wp = reinterpret_cast<const uint32_t *>(S.text) + (off >> 2);
             const int sh = (off & 3) * 8;
             uint32_t w0 = wp[0], w1 = wp[1], w2 = wp[2], w3 = wp[3], w4 = wp[4];
             uint32_t a0 = __funnelshift_r(w0, w1, sh), a1 = __funnelshift_r(w1, w2, sh);
             uint32_t a2 = __funnelshift_r(w2, w3, sh), a3 = __funnelshift_r(w3, w4, sh);
-            // zero the bytes beyond len
-            auto keep = [&](int word_idx) -> uint32_t {
-                int nb = len - 4 * word_idx;
-                return nb >= 4 ? 0xFFFFFFFFu : (nb <= 0 ? 0u : ((1u << (8 * nb)) - 1u));
-            };
-            a0 &= keep(0); a1 &= keep(1); a2 &= keep(2); a3 &= keep(3);
-            const uint64_t k0 = ((uint64_t)a1 << 32) | a0, k1 = ((uint64_t)a3 << 32) | a2;
+            // zero the bytes at and beyond len
+            const int nb0 = len >= 8 ? 64 : len * 8, nb1 = len <= 8 ? 0 : (len - 8) * 8;
+            const uint64_t mk0 = nb0 >= 64 ? ~0ull : ((1ull << nb0) - 1ull);
+            const uint64_t mk1 = nb1 >= 64 ? ~0ull : ((1ull << nb1) - 1ull);
+            const uint64_t k0 = (((uint64_t)a1 << 32) | a0) & mk0, k1 = (((uint64_t)a3 << 32) | a2) & mk1;
             const uint32_t r = piece_lookup16(T, k0, k1, (uint32_t)len);
-            if (r != RANK_MAX) { s_tok[off] = r; my_tmask |= 1u << j; }
+            if (r != RANK_MAX) { S.tok[off] = r; my_tmask |= 1u << j; }
             else {
-                uint32_t slot = atomicAdd(&s_nmiss, 1u);
-                s_miss[slot] = (uint16_t)(off | ((len - 1) << 12));
+                uint32_t slot = atomicAdd(&S.nmiss, 1u);
+                S.miss[slot] = (uint16_t)(off | ((len - 1) << 12));
             }
         }
-        if (my_tmask) atomicOr(&s_tmask[tid], my_tmask);
-        s_lmask[tid] = my_lmask;
+        if (my_tmask) atomicOr(&S.tmask[lane], my_tmask);
     }
-    __syncthreads();
+    __syncwarp();
 
-    // ---- phase B: per-thread exact merge of the pieces that missed -------------------------
+    // ---- phase B: per-lane exact merge of the pieces that missed --------------------------
     {
-        const uint32_t nmiss = s_nmiss;
-        SmemCol idc{s_id + tid}, rkc{s_rk + tid};
-        for (uint32_t i = tid; i < nmiss; i += TILE_THREADS) {
-            const uint32_t e = s_miss[i];
+        const uint32_t nmiss = S.nmiss;
+        for (uint32_t i = lane; i < nmiss; i += 32) {
+            const uint32_t e = S.miss[i];
             const int off = e & 0xFFF, len = (int)(e >> 12) + 1;
-            const uint8_t *pc = s_text + off;
-            uint32_t mask = merge_short(T, [&](int j) { return (uint32_t)pc[j]; }, len, idc, rkc);
+            const uint8_t *pc = S.text + off;
+            uint32_t id[SHORT_MAX], rk[SHORT_MAX];
+            uint32_t mask = merge_short(T, [&](int j) { return (uint32_t)pc[j]; }, len, id, rk);
             bool bad = false;
             for (uint32_t mm = mask; mm;) {
                 int j = __ffs(mm) - 1; mm &= mm - 1;
-                uint32_t id = idc[j];
-                bad |= id >= PSEUDO_BASE;
-                s_tok[off + j] = id;
+                uint32_t x = id[j];
+                bad |= x >= PSEUDO_BASE;
+                S.tok[off + j] = x;
             }
             if (bad) atomicOr(&p.ctr->err, ERR_NOBYTE);
-            // token-start bits (may straddle two words of s_tmask)
             const int wi = off >> 5, sh = off & 31;
-            atomicOr(&s_tmask[wi], mask << sh);
-            if (sh + len > 32) atomicOr(&s_tmask[wi + 1], mask >> (32 - sh));
+            atomicOr(&S.tmask[wi], mask << sh);
+            if (sh + len > 32) atomicOr(&S.tmask[wi + 1], mask >> (32 - sh));
         }
     }
-    __syncthreads();
+    __syncwarp();
 
-    // ---- phase C: count, scan, look-back --------------------------------------------------
-    const uint32_t tm = s_tmask[tid];
-    const uint32_t lm = s_lmask[tid];
-    const uint32_t extra = (tid == TILE_THREADS - 1) ? s_tmask[TILE_THREADS] : 0u;
-    uint32_t cnt = __popc(tm) + __popc(extra);
+    // ---- phase C: compact the short-piece tokens into the scratch region, publish counts ----
+    const uint32_t tm = S.tmask[lane];
+    const uint32_t extra = (lane == 31) ? S.tmask[32] : 0u;
+    const uint32_t cs = __popc(tm) + __popc(extra);
+    uint32_t cl = 0;
     for (uint32_t mm = lm; mm;) {
         int j = __ffs(mm) - 1; mm &= mm - 1;
-        long long pos = tile_byte + tid * 32 + j;
-        cnt += p.q.ntok[p.lidx[pos >> 4]];
+        long long pos = sub_byte + lane * 32 + j;
+        cl += p.q.ntok[p.lidx[pos >> 4]];
     }
-    uint32_t incl = cnt;
+    uint32_t incl = cs, tot_long = cl;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
         uint32_t y = __shfl_up_sync(0xFFFFFFFFu, incl, o);
-        if ((tid & 31) >= o) incl += y;
+        if (lane >= o) incl += y;
     }
-    if ((tid & 31) == 31) s_warp_tot[tid >> 5] = incl;
-    __syncthreads();
-    uint32_t warp_base = 0, tile_total = 0;
 #pragma unroll
-    for (int w = 0; w < TILE_THREADS / 32; w++) {
-        uint32_t x = s_warp_tot[w];
-        if (w < (tid >> 5)) warp_base += x;
-        tile_total += x;
+    for (int o = 16; o; o >>= 1) tot_long += __shfl_xor_sync(0xFFFFFFFFu, tot_long, o);
+    const uint32_t tot_short = __shfl_sync(0xFFFFFFFFu, incl, 31);
+    {
+        uint32_t *dst = p.scratch + sub * SUB_CAP + (incl - cs);
+        for (uint32_t mm = tm; mm;) { int j = __ffs(mm) - 1; mm &= mm - 1; *dst++ = S.tok[lane * 32 + j]; }
+        for (uint32_t mm = extra; mm;) { int j = __ffs(mm) - 1; mm &= mm - 1; *dst++ = S.tok[SUB_BYTES + j]; }
     }
-    const uint32_t excl = warp_base + incl - cnt;
-    if (tid == 0) {
-        unsigned long long base = 0;
-        volatile unsigned long long *st = p.tile_state;
-        if (tile == 0) {
-            st[0] = ST_INC | (unsigned long long)tile_total;
-        } else {
-            st[tile] = ST_AGG | (unsigned long long)tile_total;
-            __threadfence();
-            long long t = tile - 1;
-            for (;;) {
-                unsigned long long v = st[t];
-                if ((v >> 62) == 0) continue;               // predecessor not published yet
-                base += v & ST_MASK;
-                if (v & ST_INC) break;
-                t--;
-            }
-            st[tile] = ST_INC | (base + tile_total);
-        }
-        __threadfence();
-        s_base = base;
+    if (gw < p.n_words) p.tbits[gw] = tm;
+    const uint32_t dm = (gw < p.n_words) ? __ldg(p.dbits + gw) : 0u;
+    const uint32_t any_long = __ballot_sync(0xFFFFFFFFu, lm != 0), any_doc = __ballot_sync(0xFFFFFFFFu, dm != 0);
+    if (lane == 31) {
+        p.sub_count[sub] = tot_short + tot_long;
+        p.sub_flags[sub] = (any_long ? 1u : 0u) | (any_doc ? 2u : 0u) | ((uint32_t)__popc(extra) << 8);
     }
-    __syncthreads();
+}
 
-    // ---- phase D: write tokens and per-document offsets -----------------------------------
-    {
-        unsigned long long k = s_base + excl;
-        const uint32_t dm = (gw < p.n_words) ? p.dbits[gw] : 0u;
-        unsigned long long d = dm ? (unsigned long long)p.span_first_doc[gw] : 0ull;
-        uint32_t walk = tm | lm | dm;
-        while (walk) {
-            const int j = __ffs(walk) - 1; walk &= walk - 1;
-            const int off = tid * 32 + j;
-            const long long pos = tile_byte + off;
-            if ((dm >> j) & 1u) {
-                while (d <= p.n_docs && p.doc_off[d] == (unsigned long long)pos) { p.tok_off[d] = k; d++; }
-            }
-            if ((tm >> j) & 1u) { p.out[k++] = s_tok[off]; }
-            else if ((lm >> j) & 1u) {
-                const uint32_t qi = p.lidx[pos >> 4];
-                const uint32_t nt = p.q.ntok[qi];
-                const unsigned long long src = p.q.off[qi];
-                if (nt <= 64) { for (uint32_t x = 0; x < nt; x++) p.out[k + x] = p.ltok[src + x]; }
-                else {
-                    uint32_t slot = atomicAdd(&s_ndefer, 1u);
-                    s_defer_dst[slot] = k; s_defer_src[slot] = src; s_defer_n[slot] = nt;
-                }
-                k += nt;
-            }
+// --------------------------------------------------------------------------------------------
+// kernel 5: exclusive scan of the per-sub-tile token counts (single block; n_sub ~ N / 1024)
+// --------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) scan_counts_kernel(const uint32_t *__restrict__ cnt, long long n,
+                                                           unsigned long long *__restrict__ base) {
+    __shared__ unsigned long long s_part[1024];
+    const int tid = threadIdx.x;
+    const long long per = (n + 1023) / 1024;
+    const long long lo = tid * per, hi = (lo + per < n) ? lo + per : n;
+    unsigned long long sum = 0;
+    for (long long i = lo; i < hi; i++) sum += cnt[i];
+    s_part[tid] = sum;
+    __syncthreads();
+    for (int o = 1; o < 1024; o <<= 1) {
+        unsigned long long v = (tid >= o) ? s_part[tid - o] : 0ull;
+        __syncthreads();
+        s_part[tid] += v;
+        __syncthreads();
+    }
+    unsigned long long run = s_part[tid] - sum;
+    for (long long i = lo; i < hi; i++) { base[i] = run; run += cnt[i]; }
+    if (tid == 1023) base[n] = s_part[1023];
+}
+
+// --------------------------------------------------------------------------------------------
+// kernel 6: gather.  One warp per sub-tile: straight coalesced copy when the sub-tile has neither
+// long pieces nor document starts, otherwise the per-span walk that splices long-piece tokens in
+// and writes the per-document token offsets.
+// --------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) gather_kernel(TileParams p) {
+    const int lane = threadIdx.x & 31;
+    const long long sub = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (sub >= p.n_sub) return;
+    const unsigned long long base = p.sub_base[sub];
+    const uint32_t flags = p.sub_flags[sub];
+    const uint32_t *src = p.scratch + sub * SUB_CAP;
+    if ((flags & 3u) == 0) {
+        const uint32_t n = p.sub_count[sub];
+        for (uint32_t i = lane; i < n; i += 32) p.out[base + i] = src[i];
+        return;
+    }
+    const long long sub_byte = sub * SUB_BYTES;
+    const long long gw = sub * 32 + lane;
+    const bool in = gw < p.n_words;
+    const uint32_t tm = in ? p.tbits[gw] : 0u;
+    const uint32_t dm = in ? p.dbits[gw] : 0u;
+    const uint32_t pw = in ? p.pbits[gw] : 0u;
+    const uint32_t pw1 = (gw + 1 < p.n_words) ? p.pbits[gw + 1] : 0u;
+    const uint64_t ahead = ((uint64_t)pw1 << 32) | pw;
+    uint32_t lm = 0;
+    for (uint32_t m = pw; m;) {
+        const int j = __ffs(m) - 1; m &= m - 1;
+        if (sub_byte + lane * 32 + j >= p.n_bytes) break;
+        if (((uint32_t)((ahead >> j) >> 1) & 0xFFFFu) == 0) lm |= 1u << j;
+    }
+    const uint32_t n_extra = (lane == 31) ? (flags >> 8) : 0u;
+    const uint32_t cs = __popc(tm) + n_extra;
+    uint32_t cl = 0;
+    for (uint32_t mm = lm; mm;) {
+        int j = __ffs(mm) - 1; mm &= mm - 1;
+        cl += p.q.ntok[p.lidx[(sub_byte + lane * 32 + j) >> 4]];
+    }
+    uint32_t incl_s = cs, incl_t = cs + cl;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        uint32_t y = __shfl_up_sync(0xFFFFFFFFu, incl_s, o), z = __shfl_up_sync(0xFFFFFFFFu, incl_t, o);
+        if (lane >= o) { incl_s += y; incl_t += z; }
+    }
+    unsigned long long k = base + (incl_t - cs - cl);
+    uint32_t si = incl_s - cs;                                   // index of this lane's first short token in scratch
+    unsigned long long big_dst = 0, big_src = 0; uint32_t big_n = 0;
+    unsigned long long d = dm ? (unsigned long long)p.span_first_doc[gw] : 0ull;
+    uint32_t walk = tm | lm | dm;
+    while (walk) {
+        const int j = __ffs(walk) - 1; walk &= walk - 1;
+        const long long pos = sub_byte + lane * 32 + j;
+        if ((dm >> j) & 1u) {
+            while (d <= p.n_docs && p.doc_off[d] == (unsigned long long)pos) { p.tok_off[d] = k; d++; }
         }
-        for (uint32_t mm = extra; mm;) {
-            int j = __ffs(mm) - 1; mm &= mm - 1;
-            p.out[k++] = s_tok[TILE_BYTES + j];
+        if ((tm >> j) & 1u) { p.out[k++] = src[si++]; }
+        else if ((lm >> j) & 1u) {
+            const uint32_t qi = p.lidx[pos >> 4];
+            const uint32_t nt = p.q.ntok[qi];
+            const unsigned long long lsrc = p.q.off[qi];
+            if (nt <= 32) { for (uint32_t x = 0; x < nt; x++) p.out[k + x] = p.ltok[lsrc + x]; }
+            else { big_dst = k; big_src = lsrc; big_n = nt; }   // > 32 tokens => > 32 bytes: at most one per span
+            k += nt;
         }
     }
-    __syncthreads();
-    {
-        const uint32_t nd = s_ndefer;                      // big long pieces: whole block copies
-        for (uint32_t i = 0; i < nd; i++) {
-            const unsigned long long dst = s_defer_dst[i], src = s_defer_src[i];
-            const uint32_t nt = s_defer_n[i];
-            for (uint32_t x = tid; x < nt; x += TILE_THREADS) p.out[dst + x] = p.ltok[src + x];
-        }
+    for (uint32_t x = 0; x < n_extra; x++) p.out[k++] = src[si++];
+    for (uint32_t pending = __ballot_sync(0xFFFFFFFFu, big_n != 0); pending; pending &= pending - 1) {
+        const int src_lane = __ffs(pending) - 1;
+        const unsigned long long dst = __shfl_sync(0xFFFFFFFFu, big_dst, src_lane);
+        const unsigned long long bs = __shfl_sync(0xFFFFFFFFu, big_src, src_lane);
+        const uint32_t nt = __shfl_sync(0xFFFFFFFFu, big_n, src_lane);
+        for (uint32_t x = lane; x < nt; x += 32) p.out[dst + x] = p.ltok[bs + x];
     }
 }
 
@@ -595,14 +615,15 @@ struct b200bpe {
     DevTables T; UcTables uc;
     uint64_t table_bytes[4] = {0, 0, 0, 0};
     // workspace (grow-only)
-    DevBuf<uint8_t> w_text; DevBuf<unsigned long long> w_docoff, w_tokoff, w_tile_state;
+    DevBuf<uint8_t> w_text; DevBuf<unsigned long long> w_docoff, w_tokoff, w_sub_base;
+    DevBuf<uint32_t> w_scratch, w_tbits, w_sub_count, w_sub_flags;
     DevBuf<uint32_t> w_dbits, w_pbits, w_sfd, w_lidx, w_out, w_ltok;
     DevBuf<unsigned long long> w_lq_start, w_lq_off; DevBuf<unsigned int> w_lq_len, w_lq_ntok;
     DevBuf<uint32_t> w_idA, w_rkA, w_idB, w_rkB, w_aux1, w_aux2; DevBuf<uint8_t> w_flag;
     Counters *d_ctr = nullptr; Counters *h_ctr = nullptr;   // h_ctr pinned
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[8];
-    float last_ms[7] = {0, 0, 0, 0, 0, 0, 0};
+    float last_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     uint32_t last_launches = 0;
     std::mutex mu;
     std::vector<PinnedBuf> pinned_pool;
@@ -694,7 +715,8 @@ extern "C" void b200bpe_destroy(b200bpe_t *h) {
     cudaFree(h->d_byte_id); cudaFree(h->d_pair2); cudaFree(h->d_pair_tab); cudaFree(h->d_piece_tab);
     cudaFree(h->d_long_tab); cudaFree(h->d_long_blob); cudaFree(h->d_uc1); cudaFree(h->d_uc2); cudaFree(h->d_ascii);
     cudaFree(h->d_ctr); if (h->h_ctr) cudaFreeHost(h->h_ctr);
-    h->w_text.release(); h->w_docoff.release(); h->w_tokoff.release(); h->w_tile_state.release();
+    h->w_text.release(); h->w_docoff.release(); h->w_tokoff.release(); h->w_sub_base.release();
+    h->w_scratch.release(); h->w_tbits.release(); h->w_sub_count.release(); h->w_sub_flags.release();
     h->w_dbits.release(); h->w_pbits.release(); h->w_sfd.release(); h->w_lidx.release(); h->w_out.release();
     h->w_ltok.release(); h->w_lq_start.release(); h->w_lq_off.release(); h->w_lq_len.release(); h->w_lq_ntok.release();
     h->w_idA.release(); h->w_rkA.release(); h->w_idB.release(); h->w_rkB.release(); h->w_aux1.release();
@@ -713,11 +735,14 @@ static int run_pipeline(b200bpe *h, const uint8_t *d_text, uint64_t n_bytes, con
     if (n_bytes >= (1ull << 32) - 4096) return fail(B200BPE_EINVAL, "batch too large for one call (>= 4 GiB)");
     if (n_docs >= 0xFFFFFFFEull) return fail(B200BPE_EINVAL, "too many documents in one call");
     const long long n_words = (long long)((n_bytes + 1 + 31) / 32);
-    const long long n_tiles = (n_words + TILE_THREADS - 1) / TILE_THREADS;
+    const long long n_tiles = (n_words + 31) / 32;                  // 1 KiB sub-tiles, one warp each
     CUDA_TRY(h->w_dbits.ensure((size_t)n_words + 4));
     CUDA_TRY(h->w_pbits.ensure((size_t)n_words + 4));
     CUDA_TRY(h->w_sfd.ensure((size_t)n_words + 4));
-    CUDA_TRY(h->w_tile_state.ensure((size_t)n_tiles + 1));
+    CUDA_TRY(h->w_sub_base.ensure((size_t)n_tiles + 2));
+    CUDA_TRY(h->w_sub_count.ensure((size_t)n_tiles + 2)); CUDA_TRY(h->w_sub_flags.ensure((size_t)n_tiles + 2));
+    CUDA_TRY(h->w_tbits.ensure((size_t)n_words + 4));
+    CUDA_TRY(h->w_scratch.ensure((size_t)n_tiles * SUB_CAP + 64));
     CUDA_TRY(h->w_lidx.ensure((size_t)(n_bytes >> 4) + 4));
     const size_t qcap = (size_t)(n_bytes / (SHORT_MAX + 1)) + 4;
     CUDA_TRY(h->w_lq_start.ensure(qcap)); CUDA_TRY(h->w_lq_off.ensure(qcap));
@@ -730,7 +755,6 @@ static int run_pipeline(b200bpe *h, const uint8_t *d_text, uint64_t n_bytes, con
     CUDA_TRY(cudaMemsetAsync(h->w_dbits.p, 0, ((size_t)n_words + 4) * 4, st));
     CUDA_TRY(cudaMemsetAsync(h->w_sfd.p, 0xFF, ((size_t)n_words + 4) * 4, st));
     CUDA_TRY(cudaMemsetAsync(h->w_pbits.p + n_words, 0, 4 * 4, st));
-    CUDA_TRY(cudaMemsetAsync(h->w_tile_state.p, 0, ((size_t)n_tiles + 1) * 8, st));
     {
         unsigned long long nd1 = n_docs + 1;
         mark_docs_kernel<<<(unsigned)((nd1 + 255) / 256), 256, 0, st>>>(d_doc_off, n_docs, n_bytes, h->w_dbits.p,
@@ -778,12 +802,17 @@ static int run_pipeline(b200bpe *h, const uint8_t *d_text, uint64_t n_bytes, con
     CUDA_TRY(cudaEventRecord(h->ev[3], st));
     {
         TileParams p;
-        p.text = d_text; p.n_bytes = (long long)n_bytes; p.n_words = n_words; p.n_tiles = n_tiles;
+        p.text = d_text; p.n_bytes = (long long)n_bytes; p.n_words = n_words; p.n_sub = n_tiles;
         p.pbits = h->w_pbits.p; p.dbits = h->w_dbits.p; p.span_first_doc = h->w_sfd.p;
         p.doc_off = d_doc_off; p.n_docs = n_docs; p.q = q; p.lidx = h->w_lidx.p; p.ltok = h->w_ltok.p;
-        p.out = d_out; p.tok_off = d_tok_off; p.tile_state = h->w_tile_state.p; p.ctr = h->d_ctr;
-        encode_tiles_kernel<<<(unsigned)n_tiles, TILE_THREADS, 0, st>>>(p, h->T);
-        launches++;
+        p.scratch = h->w_scratch.p; p.tbits = h->w_tbits.p; p.sub_count = h->w_sub_count.p;
+        p.sub_flags = h->w_sub_flags.p; p.sub_base = h->w_sub_base.p;
+        p.out = d_out; p.tok_off = d_tok_off; p.ctr = h->d_ctr;
+        encode_tiles_kernel<<<(unsigned)((n_tiles + ENC_WARPS - 1) / ENC_WARPS), ENC_WARPS * 32, 0, st>>>(p, h->T);
+        CUDA_TRY(cudaEventRecord(h->ev[7], st));
+        scan_counts_kernel<<<1, 1024, 0, st>>>(h->w_sub_count.p, n_tiles, h->w_sub_base.p);
+        gather_kernel<<<(unsigned)((n_tiles + 7) / 8), 256, 0, st>>>(p);
+        launches += 3;
     }
     CUDA_TRY(cudaEventRecord(h->ev[4], st));
     CUDA_TRY(cudaMemcpyAsync(h->h_ctr, h->d_ctr, sizeof(Counters), cudaMemcpyDeviceToHost, st));
@@ -792,7 +821,8 @@ static int run_pipeline(b200bpe *h, const uint8_t *d_text, uint64_t n_bytes, con
     cudaEventElapsedTime(&h->last_ms[0], h->ev[0], h->ev[1]);
     cudaEventElapsedTime(&h->last_ms[1], h->ev[1], h->ev[2]);
     cudaEventElapsedTime(&h->last_ms[2], h->ev[2], h->ev[3]);
-    cudaEventElapsedTime(&h->last_ms[3], h->ev[3], h->ev[4]);
+    cudaEventElapsedTime(&h->last_ms[3], h->ev[3], h->ev[7]);
+    cudaEventElapsedTime(&h->last_ms[7], h->ev[7], h->ev[4]);
     cudaEventElapsedTime(&h->last_ms[4], h->ev[0], h->ev[4]);
     h->last_launches = launches;
     if (h->h_ctr->err & ERR_NOBYTE)
@@ -981,9 +1011,9 @@ extern "C" int b200bpe_decode_bytes(b200bpe_t *h, const uint32_t *tokens, uint64
     return B200BPE_OK;
 }
 
-extern "C" int b200bpe_last_timings(b200bpe_t *h, float *ms7, uint32_t *n_launches) {
+extern "C" int b200bpe_last_timings(b200bpe_t *h, float *ms8, uint32_t *n_launches) {
     if (!h) return fail(B200BPE_EINVAL, "null handle");
-    if (ms7) memcpy(ms7, h->last_ms, sizeof(h->last_ms));
+    if (ms8) memcpy(ms8, h->last_ms, sizeof(h->last_ms));
     if (n_launches) *n_launches = h->last_launches;
     return B200BPE_OK;
 }

@@ -87,17 +87,34 @@ B2_HD uint32_t pair_lookup(const DevTables &T, uint32_t a, uint32_t b) {
     }
 }
 
+// two independent pair probes with both first loads in flight together (the two neighbours of a
+// merge, src/lib.rs:182-185)
+B2_HD void pair_lookup2(const DevTables &T, uint32_t a1, uint32_t b1, uint32_t a2, uint32_t b2, uint32_t &r1,
+                        uint32_t &r2) {
+    uint32_t s1 = pair_hash(a1, b1) & T.pair_mask, s2 = pair_hash(a2, b2) & T.pair_mask;
+    U4 e1 = B2_LDG_U4(T.pair_tab + s1), e2 = B2_LDG_U4(T.pair_tab + s2);
+    for (;;) {
+        if (e1.x == a1 && e1.y == b1) { r1 = e1.z; break; }
+        if (e1.x == 0xFFFFFFFFu) { r1 = RANK_MAX; break; }
+        s1 = (s1 + 1) & T.pair_mask; e1 = B2_LDG_U4(T.pair_tab + s1);
+    }
+    for (;;) {
+        if (e2.x == a2 && e2.y == b2) { r2 = e2.z; break; }
+        if (e2.x == 0xFFFFFFFFu) { r2 = RANK_MAX; break; }
+        s2 = (s2 + 1) & T.pair_mask; e2 = B2_LDG_U4(T.pair_tab + s2);
+    }
+}
+
 // whole-piece probe for len <= 16 (src/lib.rs:367-368)
 B2_HD uint32_t piece_lookup16(const DevTables &T, uint64_t k0, uint64_t k1, uint32_t len) {
     uint32_t s = (uint32_t)piece_hash(k0, k1, len) & T.piece_mask;
     for (;;) {
-        U4 m = B2_LDG_U4(T.piece_tab + 2 * s + 1);
+        const U4 m = B2_LDG_U4(T.piece_tab + 2 * s + 1);      // both halves of the 32-byte slot: one sector
+        const U4 k = B2_LDG_U4(T.piece_tab + 2 * s);
         if (m.x == 0) return RANK_MAX;
-        if (m.x == len) {
-            U4 k = B2_LDG_U4(T.piece_tab + 2 * s);
-            if (k.x == (uint32_t)k0 && k.y == (uint32_t)(k0 >> 32) && k.z == (uint32_t)k1 && k.w == (uint32_t)(k1 >> 32))
-                return m.y;
-        }
+        if (m.x == len && k.x == (uint32_t)k0 && k.y == (uint32_t)(k0 >> 32) && k.z == (uint32_t)k1 &&
+            k.w == (uint32_t)(k1 >> 32))
+            return m.y;
         s = (s + 1) & T.piece_mask;
     }
 }
@@ -166,10 +183,18 @@ B2_HD uint32_t merge_short(const DevTables &T, ByteFn byte_at, int n, IdArr id, 
         mask &= ~(1u << j2);
         id[bj] = best;                              // id == rank of the merged token
         above &= ~(1u << j2);
-        if (above) rk[bj] = pair_lookup(T, best, id[b2_ffs(above) - 1]);
-        else rk[bj] = RANK_MAX;
-        uint32_t below = mask & ((1u << bj) - 1u);
-        if (below) { int jp = 31 - b2_clz(below); rk[jp] = pair_lookup(T, id[jp], best); }
+        const uint32_t below = mask & ((1u << bj) - 1u);
+        if (above && below) {
+            const int jp = 31 - b2_clz(below);
+            uint32_t rr, rl;
+            pair_lookup2(T, best, id[b2_ffs(above) - 1], id[jp], best, rr, rl);
+            rk[bj] = rr; rk[jp] = rl;
+        } else if (above) {
+            rk[bj] = pair_lookup(T, best, id[b2_ffs(above) - 1]);
+        } else {
+            rk[bj] = RANK_MAX;
+            if (below) { const int jp = 31 - b2_clz(below); rk[jp] = pair_lookup(T, id[jp], best); }
+        }
     }
     return mask;
 }

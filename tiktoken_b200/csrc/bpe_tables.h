@@ -99,7 +99,7 @@ inline int build_tables(const uint8_t *tok_bytes, const uint64_t *tok_off, const
         }
     }
     H.n_pairs = pairs.size();
-    uint32_t pc = pow2_at_least((uint64_t)pairs.size() * 2 + 2);
+    uint32_t pc = pow2_at_least((uint64_t)pairs.size() * 3 + 2);      // load factor <= 1/3
     H.pair_mask = pc - 1;
     H.pair_tab.assign(pc, U4{0xFFFFFFFFu, 0xFFFFFFFFu, RANK_MAX, 0});
     for (auto &p : pairs) {
@@ -107,7 +107,7 @@ inline int build_tables(const uint8_t *tok_bytes, const uint64_t *tok_off, const
         while (H.pair_tab[s].x != 0xFFFFFFFFu) s = (s + 1) & H.pair_mask;
         H.pair_tab[s] = U4{p.a, p.b, p.r, 0};
     }
-    uint32_t sc = pow2_at_least((uint64_t)n_short * 2 + 2);
+    uint32_t sc = pow2_at_least((uint64_t)n_short * 3 + 2);
     H.piece_mask = sc - 1;
     H.piece_tab.assign((size_t)sc * 2, U4{0, 0, 0, 0});
     uint32_t lc = pow2_at_least((uint64_t)n_long * 2 + 2);

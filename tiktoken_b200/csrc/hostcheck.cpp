@@ -6,6 +6,7 @@
 #include <cstring>
 #include <vector>
 #include "text_access.cuh"
+#include "pretok_fast.cuh"
 #include "unicode_classes.inc"
 
 using namespace b2bpe;
@@ -75,4 +76,34 @@ extern "C" uint32_t hc_probe_long(void *p, const uint8_t *piece, uint32_t len) {
     DevTables T = H.view();
     uint64_t h = long_hash_bytes(piece, len);
     return piece_lookup_long(T, h, len, [&](uint32_t i) { return piece[i]; });
+}
+
+// the bit-parallel span evaluator the pre-tokeniser kernel actually runs (pretok_fast.cuh)
+extern "C" int hc_piece_starts_fast(int pattern, const uint8_t *text, int64_t n, const uint64_t *doc_off,
+                                    int64_t n_docs, uint8_t *is_start /* n+1 bytes */, uint64_t *stats2) {
+    std::vector<uint8_t> padded((size_t)n + 64, 0);
+    memcpy(padded.data(), text, (size_t)n);
+    const int64_t n_words = (n + 1 + 31) / 32;
+    std::vector<uint32_t> dbits((size_t)n_words + 4, 0);
+    for (int64_t d = 0; d <= n_docs; d++) {
+        uint64_t o = doc_off[d];
+        dbits[o >> 5] |= 1u << (o & 31);
+    }
+    uint8_t ascii[128];
+    for (int i = 0; i < 128; i++) ascii[i] = UC_STAGE2[(uint32_t)UC_STAGE1[0] * 256 + i];
+    TextAccess t{padded.data(), n, dbits.data(), UC_STAGE1, UC_STAGE2, ascii};
+    SpanStats st{0, 0};
+    for (int64_t w = 0; w < n_words; w++) {
+        uint32_t word;
+        if (pattern == PAT_R50K) word = span_boundaries<PAT_R50K>(t, w, &st);
+        else if (pattern == PAT_CL100K) word = span_boundaries<PAT_CL100K>(t, w, &st);
+        else if (pattern == PAT_O200K) word = span_boundaries<PAT_O200K>(t, w, &st);
+        else return -1;
+        for (int j = 0; j < 32; j++) {
+            int64_t pos = w * 32 + j;
+            if (pos <= n) is_start[pos] = (word >> j) & 1u;
+        }
+    }
+    if (stats2) { stats2[0] = st.positions; stats2[1] = st.slow; }
+    return 0;
 }

@@ -1,0 +1,208 @@
+// pretok_fast.cuh -- bit-parallel evaluation of the pre-tokeniser rules for one 32-byte span.
+//
+// pretok_rules.cuh decides each position on its own with ~100-200 instructions.  Here a thread
+// classifies a 48-byte window (its 32 bytes, 8 before, 8 after) with SWAR byte tests, gathers
+// the classes into 64-bit masks (bit i = byte i of the window, multi-byte scalars carry their
+// class on every byte) and evaluates the rules for all 32 positions at once with shifts and
+// logic ops.  Every position whose outcome is not fully determined by that local picture
+// (contractions, digit runs of 3+, CR/LF look-ahead, o200k case/mark subtleties, multi-byte
+// neighbours, ...) is flagged `slow` and decided by the general, proven rule function
+// boundary_before<PAT>().  So the fast path never has to be complete, only right where it
+// claims to be; tests/test_pretok_rules.py checks it exhaustively against the oracle.
+#pragma once
+#include "text_access.cuh"
+
+namespace b2bpe {
+
+struct SpanStats { unsigned long long positions, slow; };
+
+#if defined(__CUDA_ARCH__)
+#define B2_CTZLL(x) (__ffsll((long long)(x)) - 1)
+#define B2_POPCLL(x) __popcll(x)
+#else
+#define B2_CTZLL(x) __builtin_ctzll(x)
+#define B2_POPCLL(x) __builtin_popcountll(x)
+#endif
+
+B2_HD uint32_t swar_ge(uint32_t y7, uint32_t n) {          // per byte: y7 (7-bit) >= n  -> 0x80 flag
+    return (y7 + (0x80u - n) * 0x01010101u) & 0x80808080u;
+}
+B2_HD uint32_t swar_gather(uint32_t flags80) {             // four 0x80 flags -> 4-bit nibble
+    return (((flags80 >> 7) * 0x00204081u) >> 21) & 0xFu;
+}
+
+struct WinMasks {
+    uint64_t valid, D, hi, cont;
+    uint64_t LU, LL, LB, M, N, NA, SP, WS, NL, APOS, SLASH, O;   // WS: non-SP non-CR/LF whitespace
+};
+
+// Classify the window [win0, win0+48).  Non-ASCII scalars are decoded one by one.
+B2_HD void classify_window(const TextAccess &t, int64_t win0, int64_t w, WinMasks &m) {
+    uint32_t W[12];
+    const int64_t n = t.n;
+#if defined(__CUDA_ARCH__)
+    if (win0 >= 0 && win0 + 48 <= (n & ~7ll)) {
+        const uint2 *p = reinterpret_cast<const uint2 *>(t.text + win0);
+#pragma unroll
+        for (int k = 0; k < 6; k++) { uint2 v = __ldg(p + k); W[2 * k] = v.x; W[2 * k + 1] = v.y; }
+    } else
+#endif
+    {
+        for (int k = 0; k < 12; k++) {
+            uint32_t x = 0;
+            for (int b = 0; b < 4; b++) {
+                int64_t pos = win0 + 4 * k + b;
+                if (pos >= 0 && pos < n) x |= (uint32_t)t.text[pos] << (8 * b);
+            }
+            W[k] = x;
+        }
+    }
+    uint64_t valid = 0xFFFFFFFFFFFFull;
+    if (win0 < 0) valid &= ~((1ull << (-win0)) - 1ull);
+    if (win0 + 48 > n) { int64_t keep = n - win0; valid &= keep <= 0 ? 0ull : ((1ull << keep) - 1ull); }
+    uint64_t hi = 0, cont = 0, al = 0, up = 0, dg = 0, sp = 0, ws = 0, nl = 0, ap = 0, sl = 0;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int k = 0; k < 12; k++) {
+        const uint32_t x = W[k];
+        const uint32_t h = x & 0x80808080u, y = x & 0x7F7F7F7Fu, yl = y | 0x20202020u;
+        const uint32_t nh = ~h;
+        const uint32_t alpha = swar_ge(yl, 'a') & ~swar_ge(yl, 'z' + 1) & nh;
+        const uint32_t upper = alpha & ~((x & 0x20202020u) << 2);
+        const uint32_t digit = swar_ge(y, '0') & ~swar_ge(y, '9' + 1) & nh;
+        const uint32_t g20 = swar_ge(y, 0x20), g21 = swar_ge(y, 0x21);
+        const uint32_t space = g20 & ~g21 & nh;
+        const uint32_t g09 = swar_ge(y, 0x09), g0a = swar_ge(y, 0x0A), g0b = swar_ge(y, 0x0B);
+        const uint32_t g0d = swar_ge(y, 0x0D), g0e = swar_ge(y, 0x0E);
+        const uint32_t newl = ((g0a & ~g0b) | (g0d & ~g0e)) & nh;
+        const uint32_t wsp = g09 & ~g0e & nh & ~newl;
+        const uint32_t apos = swar_ge(y, 0x27) & ~swar_ge(y, 0x28) & nh;
+        const uint32_t slash = swar_ge(y, 0x2F) & ~swar_ge(y, 0x30) & nh;
+        const uint32_t cnt = h & ~((x & 0x40404040u) << 1);
+        const int s = 4 * k;
+        hi |= (uint64_t)swar_gather(h) << s;       cont |= (uint64_t)swar_gather(cnt) << s;
+        al |= (uint64_t)swar_gather(alpha) << s;   up |= (uint64_t)swar_gather(upper) << s;
+        dg |= (uint64_t)swar_gather(digit) << s;   sp |= (uint64_t)swar_gather(space) << s;
+        ws |= (uint64_t)swar_gather(wsp) << s;     nl |= (uint64_t)swar_gather(newl) << s;
+        ap |= (uint64_t)swar_gather(apos) << s;    sl |= (uint64_t)swar_gather(slash) << s;
+    }
+    m.valid = valid; m.hi = hi & valid; m.cont = cont & valid;
+    m.LU = up & valid; m.LL = (al & ~up) & valid; m.LB = 0; m.M = 0;
+    m.N = dg & valid; m.NA = m.N; m.SP = sp & valid; m.WS = ws & valid; m.NL = nl & valid;
+    m.APOS = ap & valid; m.SLASH = sl & valid;
+    uint64_t ascii_known = m.LU | m.LL | m.N | m.SP | m.WS | m.NL | m.APOS | m.SLASH;
+    m.O = valid & ~m.hi & ~ascii_known;
+    // doc-start bits of the window: words w-1 (top byte), w, w+1 (low byte)
+    uint64_t D = (uint64_t)t.dbits[w] << 8;
+    if (w > 0) D |= (uint64_t)(t.dbits[w - 1] >> 24);
+    D |= (uint64_t)(t.dbits[w + 1] & 0xFFu) << 40;
+    m.D = D & valid;
+    // non-ASCII scalars: decode, look up, paint the class on all their bytes
+    for (uint64_t leads = m.hi & ~m.cont; leads;) {
+        const int j = B2_CTZLL(leads); leads &= leads - 1;
+        const int64_t pos = win0 + j;
+        const unsigned b = t.text[pos];
+        const int len = b < 0xE0 ? 2 : b < 0xF0 ? 3 : 4;
+        if (pos + len > n) continue;                 // truncated tail: stays "unknown", handled by slow path
+        const int c = t.cls(pos);
+        uint64_t bits = ((1ull << len) - 1ull) << j;
+        bits &= valid;
+        switch (c) {
+            case C_LU: m.LU |= bits; break;
+            case C_LL: m.LL |= bits; break;
+            case C_LB: m.LB |= bits; break;
+            case C_M: m.M |= bits; break;
+            case C_N: m.N |= bits; break;
+            case C_WS: m.WS |= bits; break;
+            default: m.O |= bits; break;
+        }
+    }
+}
+
+template <int PAT>
+B2_HD uint32_t span_boundaries(const TextAccess &t, int64_t w, SpanStats *stats = nullptr) {
+    const int64_t base = w * 32, win0 = base - 8;
+    if (base > t.n) return 0;
+    WinMasks m;
+    classify_window(t, win0, w, m);
+    const uint64_t OWN = 0xFFFFFFFFull << 8;
+    const uint64_t lead = m.valid & ~m.cont;
+    const uint64_t own = OWN & lead & ~m.D;              // positions to decide (doc starts are forced)
+    const uint64_t L = m.LU | m.LL | m.LB;
+    const uint64_t WSnn = m.SP | m.WS;                   // whitespace that is not CR/LF
+    const uint64_t WSany = WSnn | m.NL;
+    const uint64_t aposNear = (m.APOS << 2) | (m.APOS << 3);
+    // "next scalar exists in this document and is not whitespace", for single-byte current scalars
+    const uint64_t nextNonWs = ((m.valid & ~m.D & ~WSany) >> 1);
+    const uint64_t pL = L << 1, pN = m.N << 1, pSP = m.SP << 1, pNL = m.NL << 1, pWSnn = WSnn << 1;
+    const uint64_t pWSany = WSany << 1, pAPOS = m.APOS << 1, pHi = m.hi << 1;
+    uint64_t b = 0, slow = 0;
+    if (PAT == PAT_R50K) {
+        const uint64_t X = m.O | m.APOS | m.SLASH | m.M;
+        const uint64_t pX = X << 1;
+        b |= WSany & (~pWSany | nextNonWs);
+        slow |= WSany & m.hi & pWSany;
+        b |= L & ~(pL | pSP);
+        slow |= L & (pAPOS | (pL & aposNear));
+        b |= m.N & ~(pN | pSP);
+        b |= X & ~(pX | pSP);
+    } else if (PAT == PAT_CL100K) {
+        const uint64_t X = m.O | m.APOS | m.SLASH | m.M;
+        const uint64_t pX = X << 1;
+        // letters
+        b |= L & (pN | pNL);
+        b |= L & pX & ~pHi & ~(m.D << 1) & ((X | m.SP) << 2);
+        slow |= L & ((pX & pHi) | pAPOS | (pL & aposNear));
+        // digits: groups of three from the run start
+        b |= m.N & ~pN;
+        {
+            const uint64_t a1 = m.NA << 1, a2 = m.NA << 2, n2 = m.N << 2, n3 = m.N << 3;
+            const uint64_t k1 = a1 & ~n2, k2 = a1 & a2 & ~n3;
+            slow |= m.N & pN & ~(k1 | k2);
+        }
+        b |= X & ~(pX | pSP);
+        b |= m.NL & (pL | pN);
+        b |= WSnn & ~pWSany;
+        b |= WSnn & pWSnn & nextNonWs;
+        slow |= WSnn & (pNL | (m.hi & pWSany));
+    } else {
+        const uint64_t Xo = m.O | m.APOS | m.SLASH;
+        const uint64_t pXo = Xo << 1, pM = m.M << 1, pLB = m.LB << 1, pLL = m.LL << 1, pLU = m.LU << 1;
+        const uint64_t low = m.LL | m.LB;                           // extends any word
+        b |= low & (pN | pNL);
+        slow |= low & (pXo | pM | (pL & aposNear));
+        b |= m.LU & (pLL | pN | pNL);
+        slow |= m.LU & (pLB | pM | pXo | ((pLL | pLU) & aposNear));
+        slow |= m.M | m.APOS | m.SLASH;
+        b |= m.O & (pL | pN | ((m.WS | m.NL) << 1));
+        slow |= m.O & (pM | (m.SLASH << 1));
+        b |= m.N & ~pN;
+        {
+            const uint64_t a1 = m.NA << 1, a2 = m.NA << 2, n2 = m.N << 2, n3 = m.N << 3;
+            const uint64_t k1 = a1 & ~n2, k2 = a1 & a2 & ~n3;
+            slow |= m.N & pN & ~(k1 | k2);
+        }
+        b |= m.NL & (pL | pN);
+        slow |= m.NL & pM;
+        b |= WSnn & ~pWSany;
+        b |= WSnn & pWSnn & nextNonWs;
+        slow |= WSnn & (pNL | (m.hi & pWSany));
+    }
+    // anything that touches an undecoded (truncated / unknown) non-ASCII byte goes the slow way
+    const uint64_t known = m.LU | m.LL | m.LB | m.M | m.N | m.SP | m.WS | m.NL | m.APOS | m.SLASH | m.O;
+    const uint64_t unk = m.valid & ~known;
+    slow |= unk | (unk << 1) | (unk << 2) | (unk << 3) | (unk >> 1);
+    slow &= own;
+    b = (b & own & ~slow) | (m.D & OWN);
+    for (uint64_t s = slow; s;) {
+        const int j = B2_CTZLL(s); s &= s - 1;
+        if (boundary_before<PAT>(t, win0 + j)) b |= 1ull << j;
+    }
+    if (stats) { stats->positions += (unsigned long long)B2_POPCLL(own); stats->slow += (unsigned long long)B2_POPCLL(slow); }
+    uint32_t word = (uint32_t)(b >> 8);
+    if (t.n >= base && t.n < base + 32) word |= 1u << (t.n - base);      // end sentinel
+    return word;
+}
+
+}  // namespace b2bpe
