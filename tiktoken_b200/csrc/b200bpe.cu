@@ -328,6 +328,18 @@ struct WarpSmem {
     uint32_t nmiss;
     uint32_t tok[SUB_BYTES + SHORT_MAX];
     uint16_t miss[SUB_BYTES / 2];
+    union {                            // phase A uses plist, phase B (after a __syncwarp) the merge state
+        uint16_t plist[SUB_BYTES + 2]; // piece start offsets of the sub-tile, in order, + end sentinel
+        struct {
+            uint32_t mid[SHORT_MAX * 16];  // merge state of up to 16 concurrently merged pieces: [part][slot]
+            uint32_t mrk[SHORT_MAX * 16];
+        };
+    };
+};
+
+struct SmemCol16 {                     // one slot's column of a [SHORT_MAX][16] shared array
+    uint32_t *base;
+    __device__ __forceinline__ uint32_t &operator[](int j) const { return base[j * 16]; }
 };
 
 __global__ void __launch_bounds__(ENC_WARPS * 32) encode_tiles_kernel(TileParams p, DevTables T) {
@@ -356,71 +368,107 @@ __global__ void __launch_bounds__(ENC_WARPS * 32) encode_tiles_kernel(TileParams
     {
         S.p[lane] = (gw < p.n_words) ? __ldg(p.pbits + gw) : 0u;
         if (lane < 2) { long long w2 = sub * 32 + 32 + lane; S.p[32 + lane] = (w2 < p.n_words) ? __ldg(p.pbits + w2) : 0u; }
-        S.tmask[lane] = 0;
         if (lane == 0) { S.tmask[32] = 0; S.nmiss = 0; }
     }
     __syncwarp();
 
-    // ---- phase A: whole-piece probe of every piece that starts in this lane's span --------
-    uint32_t lm = 0;                                   // long-piece starts in this span
+    // ---- piece list: compact the piece starts of the sub-tile so that the probe loop below runs
+    //      with all 32 lanes busy whatever the distribution of pieces over the spans ----------
+    uint32_t pv = S.p[lane];
     {
-        uint32_t m = S.p[lane];
-        const uint64_t ahead = ((uint64_t)S.p[lane + 1] << 32) | m;
-        uint32_t my_tmask = 0;
-        while (m) {
-            const int j = __ffs(m) - 1; m &= m - 1;
-            const int off = lane * 32 + j;
-            if (sub_byte + off >= p.n_bytes) break;
-            const uint32_t near = (uint32_t)((ahead >> j) >> 1) & 0xFFFFu;   // piece starts in the next 16 bytes
-            if (near == 0) { lm |= 1u << j; continue; }                       // > 16 bytes: long path
-            const int len = __ffs(near);
-            if (len == 1) {
-                uint32_t id = __ldg(T.byte_id + S.text[off]);
-                if (id >= PSEUDO_BASE) atomicOr(&p.ctr->err, ERR_NOBYTE);
-                S.tok[off] = id; my_tmask |= 1u << j;
-                continue;
-            }
-            const uint32_t *wp = reinterpret_cast<const uint32_t *>(S.text) + (off >> 2);
-            const int sh = (off & 3) * 8;
-            uint32_t w0 = wp[0], w1 = wp[1], w2 = wp[2], w3 = wp[3], w4 = wp[4];
-            uint32_t a0 = __funnelshift_r(w0, w1, sh), a1 = __funnelshift_r(w1, w2, sh);
-            uint32_t a2 = __funnelshift_r(w2, w3, sh), a3 = __funnelshift_r(w3, w4, sh);
-            // zero the bytes at and beyond len
-            const int nb0 = len >= 8 ? 64 : len * 8, nb1 = len <= 8 ? 0 : (len - 8) * 8;
-            const uint64_t mk0 = nb0 >= 64 ? ~0ull : ((1ull << nb0) - 1ull);
-            const uint64_t mk1 = nb1 >= 64 ? ~0ull : ((1ull << nb1) - 1ull);
-            const uint64_t k0 = (((uint64_t)a1 << 32) | a0) & mk0, k1 = (((uint64_t)a3 << 32) | a2) & mk1;
-            const uint32_t r = piece_lookup16(T, k0, k1, (uint32_t)len);
-            if (r != RANK_MAX) { S.tok[off] = r; my_tmask |= 1u << j; }
-            else {
-                uint32_t slot = atomicAdd(&S.nmiss, 1u);
-                S.miss[slot] = (uint16_t)(off | ((len - 1) << 12));
-            }
+        const long long span0 = sub_byte + lane * 32;
+        if (span0 + 32 > p.n_bytes) {                      // drop the end sentinel / bits beyond the text
+            const long long keep = p.n_bytes - span0;
+            pv = keep <= 0 ? 0u : (pv & ((1u << keep) - 1u));
         }
-        if (my_tmask) atomicOr(&S.tmask[lane], my_tmask);
+    }
+    uint32_t np;
+    {
+        const uint32_t c = __popc(pv);
+        uint32_t inc = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t y = __shfl_up_sync(0xFFFFFFFFu, inc, o);
+            if (lane >= o) inc += y;
+        }
+        np = __shfl_sync(0xFFFFFFFFu, inc, 31);
+        uint16_t *dst = S.plist + (inc - c);
+        for (uint32_t m = pv; m;) { const int j = __ffs(m) - 1; m &= m - 1; *dst++ = (uint16_t)(lane * 32 + j); }
+        if (lane == 0) {                                   // end sentinel: next piece start (or "far away")
+            const uint32_t nx = S.p[32];
+            const long long tail = p.n_bytes - sub_byte;           // text ends inside this sub-tile?
+            S.plist[np] = (uint16_t)(tail <= SUB_BYTES ? tail : (nx ? SUB_BYTES + __ffs(nx) - 1 : SUB_BYTES + 32));
+        }
+        S.tmask[lane] = pv;                                // every piece start is a token start until proven otherwise
     }
     __syncwarp();
 
-    // ---- phase B: per-lane exact merge of the pieces that missed --------------------------
+    // ---- phase A: whole-piece probe (src/lib.rs:367-368), one piece per lane per iteration -------
+    uint32_t cl = 0;                                       // tokens of long pieces met by this lane
+    for (uint32_t i = lane; i < np; i += 32) {
+        const int off = S.plist[i];
+        const int len = (int)S.plist[i + 1] - off;
+        if (len > SHORT_MAX) {                             // long path: precomputed by long_piece_kernel
+            atomicAnd(&S.tmask[off >> 5], ~(1u << (off & 31)));
+            cl += p.q.ntok[p.lidx[(sub_byte + off) >> 4]];
+            continue;
+        }
+        if (len == 1) {
+            const uint32_t id = __ldg(T.byte_id + S.text[off]);
+            if (id >= PSEUDO_BASE) atomicOr(&p.ctr->err, ERR_NOBYTE);
+            S.tok[off] = id;
+            continue;
+        }
+        const uint32_t *wp = reinterpret_cast<const uint32_t *>(S.text) + (off >> 2);
+        const int sh = (off & 3) * 8;
+        const uint32_t w0 = wp[0], w1 = wp[1], w2 = wp[2], w3 = wp[3], w4 = wp[4];
+        const uint32_t a0 = __funnelshift_r(w0, w1, sh), a1 = __funnelshift_r(w1, w2, sh);
+        const uint32_t a2 = __funnelshift_r(w2, w3, sh), a3 = __funnelshift_r(w3, w4, sh);
+        const int nb0 = len >= 8 ? 64 : len * 8, nb1 = len <= 8 ? 0 : (len - 8) * 8;
+        const uint64_t mk0 = nb0 >= 64 ? ~0ull : ((1ull << nb0) - 1ull);
+        const uint64_t mk1 = nb1 >= 64 ? ~0ull : ((1ull << nb1) - 1ull);
+        const uint64_t k0 = (((uint64_t)a1 << 32) | a0) & mk0, k1 = (((uint64_t)a3 << 32) | a2) & mk1;
+        const uint32_t r = piece_lookup16(T, k0, k1, (uint32_t)len);
+        if (r != RANK_MAX) S.tok[off] = r;
+        else {
+            atomicAnd(&S.tmask[off >> 5], ~(1u << (off & 31)));
+            const uint32_t slot = atomicAdd(&S.nmiss, 1u);
+            S.miss[slot] = (uint16_t)(off | ((len - 1) << 12));
+        }
+    }
+    __syncwarp();
+
+    // ---- phase B: exact merge of the pieces that missed; lanes 0..15 take one piece each per pass
+    //      and walk one convergent instruction stream (merge_short_conv) --------------------------
     {
         const uint32_t nmiss = S.nmiss;
-        for (uint32_t i = lane; i < nmiss; i += 32) {
-            const uint32_t e = S.miss[i];
-            const int off = e & 0xFFF, len = (int)(e >> 12) + 1;
-            const uint8_t *pc = S.text + off;
-            uint32_t id[SHORT_MAX], rk[SHORT_MAX];
-            uint32_t mask = merge_short(T, [&](int j) { return (uint32_t)pc[j]; }, len, id, rk);
-            bool bad = false;
-            for (uint32_t mm = mask; mm;) {
-                int j = __ffs(mm) - 1; mm &= mm - 1;
-                uint32_t x = id[j];
-                bad |= x >= PSEUDO_BASE;
-                S.tok[off + j] = x;
+        SmemCol16 id{S.mid + (lane & 15)}, rk{S.mrk + (lane & 15)};
+        if (lane < 16) {
+            for (uint32_t i0 = 0; i0 < nmiss; i0 += 16) {
+                const uint32_t i = i0 + lane;
+                const bool have = i < nmiss;
+                const uint32_t e = have ? S.miss[i] : 0u;
+                const int off = e & 0xFFF, len = have ? (int)(e >> 12) + 1 : 0;
+                int n_max = len;
+#pragma unroll
+                for (int o = 8; o; o >>= 1) n_max = max(n_max, __shfl_xor_sync(0x0000FFFFu, n_max, o));
+                const uint8_t *pc = S.text + off;
+                const uint32_t mask = merge_short_conv(T, [&](int j) { return (uint32_t)pc[j]; }, len, n_max,
+                                                       0x0000FFFFu, id, rk);
+                if (have) {
+                    bool bad = false;
+                    for (uint32_t mm = mask; mm;) {
+                        int j = __ffs(mm) - 1; mm &= mm - 1;
+                        uint32_t x = id[j];
+                        bad |= x >= PSEUDO_BASE;
+                        S.tok[off + j] = x;
+                    }
+                    if (bad) atomicOr(&p.ctr->err, ERR_NOBYTE);
+                    const int wi = off >> 5, sh = off & 31;
+                    atomicOr(&S.tmask[wi], mask << sh);
+                    if (sh + len > 32) atomicOr(&S.tmask[wi + 1], mask >> (32 - sh));
+                }
             }
-            if (bad) atomicOr(&p.ctr->err, ERR_NOBYTE);
-            const int wi = off >> 5, sh = off & 31;
-            atomicOr(&S.tmask[wi], mask << sh);
-            if (sh + len > 32) atomicOr(&S.tmask[wi + 1], mask >> (32 - sh));
         }
     }
     __syncwarp();
@@ -429,12 +477,6 @@ __global__ void __launch_bounds__(ENC_WARPS * 32) encode_tiles_kernel(TileParams
     const uint32_t tm = S.tmask[lane];
     const uint32_t extra = (lane == 31) ? S.tmask[32] : 0u;
     const uint32_t cs = __popc(tm) + __popc(extra);
-    uint32_t cl = 0;
-    for (uint32_t mm = lm; mm;) {
-        int j = __ffs(mm) - 1; mm &= mm - 1;
-        long long pos = sub_byte + lane * 32 + j;
-        cl += p.q.ntok[p.lidx[pos >> 4]];
-    }
     uint32_t incl = cs, tot_long = cl;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -451,7 +493,7 @@ __global__ void __launch_bounds__(ENC_WARPS * 32) encode_tiles_kernel(TileParams
     }
     if (gw < p.n_words) p.tbits[gw] = tm;
     const uint32_t dm = (gw < p.n_words) ? __ldg(p.dbits + gw) : 0u;
-    const uint32_t any_long = __ballot_sync(0xFFFFFFFFu, lm != 0), any_doc = __ballot_sync(0xFFFFFFFFu, dm != 0);
+    const uint32_t any_long = tot_long, any_doc = __ballot_sync(0xFFFFFFFFu, dm != 0);
     if (lane == 31) {
         p.sub_count[sub] = tot_short + tot_long;
         p.sub_flags[sub] = (any_long ? 1u : 0u) | (any_doc ? 2u : 0u) | ((uint32_t)__popc(extra) << 8);

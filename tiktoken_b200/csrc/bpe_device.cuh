@@ -199,4 +199,77 @@ B2_HD uint32_t merge_short(const DevTables &T, ByteFn byte_at, int n, IdArr id, 
     return mask;
 }
 
+// ------------------------------------------------------------------------------------------
+// Warp-convergent form of merge_short for the encode kernel: every lane of `group` (a lane mask)
+// merges its own piece, but all lanes walk the SAME instruction stream -- fixed trip counts
+// (n_max = longest piece in the group), selects instead of data-dependent branches -- so the
+// warp issues one stream per round instead of one per lane.  Same result as merge_short
+// (hostcheck runs both against the oracle).  A lane with n == 0 just idles along.
+// ------------------------------------------------------------------------------------------
+#if defined(__CUDA_ARCH__)
+#define B2_ANY(group, pred) __any_sync(group, pred)
+#else
+#define B2_ANY(group, pred) (pred)
+#endif
+
+template <class ByteFn, class IdArr, class RkArr>
+B2_HD uint32_t merge_short_conv(const DevTables &T, ByteFn byte_at, int n, int n_max, unsigned group,
+                                IdArr id, RkArr rk) {
+    for (int j = 0; j < n_max; j++) {
+        uint32_t i0 = 0, r0 = RANK_MAX;
+        if (j < n) {
+            const uint32_t b0 = byte_at(j);
+            i0 = B2_LDG_U32(T.byte_id + b0);
+            if (j + 1 < n) r0 = B2_LDG_U32(T.pair2 + (b0 << 8 | byte_at(j + 1)));
+        }
+        id[j] = i0; rk[j] = r0;
+    }
+    uint32_t mask = n <= 0 ? 0u : ((n >= 32) ? 0xFFFFFFFFu : ((1u << n) - 1u));
+    for (;;) {
+        uint32_t best = RANK_MAX; int bj = 0;
+        for (int j = 0; j < n_max; j++) {                      // dead / absent parts hold RANK_MAX
+            const uint32_t r = rk[j];
+            const bool lt = r < best;
+            best = lt ? r : best; bj = lt ? j : bj;
+        }
+        const bool act = best != RANK_MAX;
+        if (!B2_ANY(group, act)) break;
+        uint32_t a1 = 0, b1 = 0, a2 = 0, b2 = 0; bool need_r = false, need_l = false; int jp = 0;
+        if (act) {
+            uint32_t above = mask & ~((2u << bj) - 1u);
+            const int j2 = b2_ffs(above) - 1;
+            mask &= ~(1u << j2);
+            rk[j2] = RANK_MAX;                                 // the right part disappears
+            id[bj] = best;
+            above &= ~(1u << j2);
+            const uint32_t below = mask & ((1u << bj) - 1u);
+            if (above) { need_r = true; a1 = best; b1 = id[b2_ffs(above) - 1]; }
+            if (below) { need_l = true; jp = 31 - b2_clz(below); a2 = id[jp]; b2 = best; }
+        }
+        // the two neighbour probes of every active lane, issued together
+        uint32_t s1 = pair_hash(a1, b1) & T.pair_mask, s2 = pair_hash(a2, b2) & T.pair_mask;
+        uint32_t r1 = RANK_MAX, r2 = RANK_MAX;
+        bool p1 = need_r, p2 = need_l;
+        while (B2_ANY(group, p1 || p2)) {
+            if (p1) {
+                const U4 e = B2_LDG_U4(T.pair_tab + s1);
+                if (e.x == a1 && e.y == b1) { r1 = e.z; p1 = false; }
+                else if (e.x == 0xFFFFFFFFu) p1 = false;
+                else s1 = (s1 + 1) & T.pair_mask;
+            }
+            if (p2) {
+                const U4 e = B2_LDG_U4(T.pair_tab + s2);
+                if (e.x == a2 && e.y == b2) { r2 = e.z; p2 = false; }
+                else if (e.x == 0xFFFFFFFFu) p2 = false;
+                else s2 = (s2 + 1) & T.pair_mask;
+            }
+        }
+        if (act) {
+            rk[bj] = need_r ? r1 : RANK_MAX;
+            if (need_l) rk[jp] = r2;
+        }
+    }
+    return mask;
+}
+
 }  // namespace b2bpe

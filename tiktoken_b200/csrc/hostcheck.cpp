@@ -63,8 +63,12 @@ extern "C" int hc_encode_short(void *p, const uint8_t *piece, uint32_t len, uint
     uint32_t r = piece_lookup16(T, k0, k1, len);
     if (r != RANK_MAX) { out[0] = r; return 1; }
     if (len == 1) { uint32_t id = T.byte_id[piece[0]]; out[0] = id >= PSEUDO_BASE ? RANK_MAX : id; return 1; }
-    uint32_t id[32], rk[32];
+    uint32_t id[32], rk[32], id2[32], rk2[32];
     uint32_t mask = merge_short(T, [&](int j) { return (uint32_t)piece[j]; }, (int)len, id, rk);
+    // the warp-convergent variant the kernel uses must agree (n_max > n exercises the padding)
+    uint32_t mask2 = merge_short_conv(T, [&](int j) { return (uint32_t)piece[j]; }, (int)len, SHORT_MAX, 1u, id2, rk2);
+    if (mask2 != mask) return -2;
+    for (uint32_t m = mask; m;) { int j = __builtin_ffs(m) - 1; m &= m - 1; if (id[j] != id2[j]) return -2; }
     int k = 0;
     for (uint32_t m = mask; m;) { int j = __builtin_ffs(m) - 1; m &= m - 1; out[k++] = id[j] >= PSEUDO_BASE ? RANK_MAX : id[j]; }
     return k;
