@@ -20,6 +20,7 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <algorithm>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -57,6 +58,7 @@ struct Counters {            // device-resident, zeroed per call
     unsigned int long_head;
     unsigned int ticket;
     unsigned int err;
+    unsigned long long total_tokens;
 };
 
 struct LongQ {               // queue of pieces longer than SHORT_MAX bytes
@@ -504,7 +506,7 @@ __global__ void __launch_bounds__(ENC_WARPS * 32) encode_tiles_kernel(TileParams
 // kernel 5: exclusive scan of the per-sub-tile token counts (single block; n_sub ~ N / 1024)
 // --------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(1024) scan_counts_kernel(const uint32_t *__restrict__ cnt, long long n,
-                                                           unsigned long long *__restrict__ base) {
+                                                           unsigned long long *__restrict__ base, Counters *ctr) {
     __shared__ unsigned long long s_part[1024];
     const int tid = threadIdx.x;
     const long long per = (n + 1023) / 1024;
@@ -521,7 +523,13 @@ __global__ void __launch_bounds__(1024) scan_counts_kernel(const uint32_t *__res
     }
     unsigned long long run = s_part[tid] - sum;
     for (long long i = lo; i < hi; i++) { base[i] = run; run += cnt[i]; }
-    if (tid == 1023) base[n] = s_part[1023];
+    if (tid == 1023) { base[n] = s_part[1023]; ctr->total_tokens = s_part[1023]; }
+}
+
+// chunked host path: rebase a slice of the caller's document offsets / globalise token offsets
+__global__ void add_offset_kernel(unsigned long long *a, unsigned long long n, long long delta) {
+    unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
+    if (i < n) a[i] = (unsigned long long)((long long)a[i] + delta);
 }
 
 // --------------------------------------------------------------------------------------------
@@ -634,6 +642,43 @@ struct PinnedBuf {
 
 }  // namespace
 
+// One pipeline slot: a stream, its events and a grow-only workspace.  The host path keeps
+// three slots in flight (H2D of chunk c+1, kernels of chunk c, D2H of chunk c-1).
+struct Slot {
+    DevBuf<uint8_t> w_text; DevBuf<unsigned long long> w_docoff, w_tokoff, w_sub_base;
+    DevBuf<uint32_t> w_scratch, w_tbits, w_sub_count, w_sub_flags;
+    DevBuf<uint32_t> w_dbits, w_pbits, w_sfd, w_lidx, w_out, w_ltok;
+    DevBuf<unsigned long long> w_lq_start, w_lq_off; DevBuf<unsigned int> w_lq_len, w_lq_ntok;
+    DevBuf<uint32_t> w_idA, w_rkA, w_idB, w_rkB, w_aux1, w_aux2; DevBuf<uint8_t> w_flag;
+    Counters *d_ctr = nullptr; Counters *h_ctr = nullptr;   // h_ctr pinned
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[8];
+    float last_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    uint32_t last_launches = 0;
+    bool ok = false;
+
+    cudaError_t init() {
+        cudaError_t e = cudaMalloc((void **)&d_ctr, sizeof(Counters));
+        if (e == cudaSuccess) e = cudaHostAlloc((void **)&h_ctr, sizeof(Counters), cudaHostAllocDefault);
+        if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking);
+        for (int i = 0; i < 8 && e == cudaSuccess; i++) e = cudaEventCreate(&ev[i]);
+        ok = (e == cudaSuccess);
+        return e;
+    }
+    void destroy() {
+        w_text.release(); w_docoff.release(); w_tokoff.release(); w_sub_base.release();
+        w_scratch.release(); w_tbits.release(); w_sub_count.release(); w_sub_flags.release();
+        w_dbits.release(); w_pbits.release(); w_sfd.release(); w_lidx.release(); w_out.release(); w_ltok.release();
+        w_lq_start.release(); w_lq_off.release(); w_lq_len.release(); w_lq_ntok.release();
+        w_idA.release(); w_rkA.release(); w_idB.release(); w_rkB.release(); w_aux1.release(); w_aux2.release();
+        w_flag.release();
+        if (d_ctr) cudaFree(d_ctr);
+        if (h_ctr) cudaFreeHost(h_ctr);
+        if (ok) { for (int i = 0; i < 8; i++) cudaEventDestroy(ev[i]); }
+        if (stream) cudaStreamDestroy(stream);
+    }
+};
+
 struct b200bpe_result {
     b200bpe *owner = nullptr;
     PinnedBuf tok, off;                 // pinned when produced by the engine
@@ -656,17 +701,11 @@ struct b200bpe {
     uint16_t *d_uc1 = nullptr; uint8_t *d_uc2 = nullptr, *d_ascii = nullptr;
     DevTables T; UcTables uc;
     uint64_t table_bytes[4] = {0, 0, 0, 0};
-    // workspace (grow-only)
-    DevBuf<uint8_t> w_text; DevBuf<unsigned long long> w_docoff, w_tokoff, w_sub_base;
-    DevBuf<uint32_t> w_scratch, w_tbits, w_sub_count, w_sub_flags;
-    DevBuf<uint32_t> w_dbits, w_pbits, w_sfd, w_lidx, w_out, w_ltok;
-    DevBuf<unsigned long long> w_lq_start, w_lq_off; DevBuf<unsigned int> w_lq_len, w_lq_ntok;
-    DevBuf<uint32_t> w_idA, w_rkA, w_idB, w_rkB, w_aux1, w_aux2; DevBuf<uint8_t> w_flag;
-    Counters *d_ctr = nullptr; Counters *h_ctr = nullptr;   // h_ctr pinned
-    cudaStream_t stream = nullptr;
-    cudaEvent_t ev[8];
+    static const int N_SLOTS = 3;
+    Slot slots[3];
     float last_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     uint32_t last_launches = 0;
+    size_t chunk_bytes = 64u << 20;
     std::mutex mu;
     std::vector<PinnedBuf> pinned_pool;
 
@@ -732,10 +771,8 @@ extern "C" int b200bpe_create(const uint8_t *tok_bytes, const uint64_t *tok_off,
     if (e == cudaSuccess) e = upload(&h->d_uc1, UC_STAGE1, sizeof(UC_STAGE1));
     if (e == cudaSuccess) e = upload(&h->d_uc2, UC_STAGE2, sizeof(UC_STAGE2));
     if (e == cudaSuccess) e = upload(&h->d_ascii, ascii, 128);
-    if (e == cudaSuccess) e = cudaMalloc((void **)&h->d_ctr, sizeof(Counters));
-    if (e == cudaSuccess) e = cudaHostAlloc((void **)&h->h_ctr, sizeof(Counters), cudaHostAllocDefault);
-    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
-    for (int i = 0; i < 8 && e == cudaSuccess; i++) e = cudaEventCreate(&h->ev[i]);
+    for (int i = 0; i < b200bpe::N_SLOTS && e == cudaSuccess; i++) e = h->slots[i].init();
+    if (const char *cm = getenv("B200BPE_CHUNK_MB")) { long v = atol(cm); if (v >= 1 && v <= 2048) h->chunk_bytes = (size_t)v << 20; }
     if (e != cudaSuccess) { std::string m = cudaGetErrorString(e); delete h; return fail(B200BPE_ECUDA, "table upload: " + m); }
     h->T.byte_id = h->d_byte_id; h->T.pair2 = h->d_pair2;
     h->T.pair_tab = h->d_pair_tab; h->T.pair_mask = H.pair_mask;
@@ -756,118 +793,126 @@ extern "C" void b200bpe_destroy(b200bpe_t *h) {
     cudaSetDevice(h->device);
     cudaFree(h->d_byte_id); cudaFree(h->d_pair2); cudaFree(h->d_pair_tab); cudaFree(h->d_piece_tab);
     cudaFree(h->d_long_tab); cudaFree(h->d_long_blob); cudaFree(h->d_uc1); cudaFree(h->d_uc2); cudaFree(h->d_ascii);
-    cudaFree(h->d_ctr); if (h->h_ctr) cudaFreeHost(h->h_ctr);
-    h->w_text.release(); h->w_docoff.release(); h->w_tokoff.release(); h->w_sub_base.release();
-    h->w_scratch.release(); h->w_tbits.release(); h->w_sub_count.release(); h->w_sub_flags.release();
-    h->w_dbits.release(); h->w_pbits.release(); h->w_sfd.release(); h->w_lidx.release(); h->w_out.release();
-    h->w_ltok.release(); h->w_lq_start.release(); h->w_lq_off.release(); h->w_lq_len.release(); h->w_lq_ntok.release();
-    h->w_idA.release(); h->w_rkA.release(); h->w_idB.release(); h->w_rkB.release(); h->w_aux1.release();
-    h->w_aux2.release(); h->w_flag.release();
+    for (int i = 0; i < b200bpe::N_SLOTS; i++) h->slots[i].destroy();
     for (auto &b : h->pinned_pool) cudaFreeHost(b.p);
-    for (int i = 0; i < 8; i++) cudaEventDestroy(h->ev[i]);
-    if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
 }
 
 // The device pipeline.  All pointers are device pointers on h->device; d_text must be 16-byte
 // aligned.  Caller holds h->mu.  `single_piece`: treat the whole buffer as one piece (no regex).
-static int run_pipeline(b200bpe *h, const uint8_t *d_text, uint64_t n_bytes, const unsigned long long *d_doc_off,
+static int finish_pipeline(b200bpe *h, Slot &S, cudaStream_t st);
+
+// Batches up to this size get their long-piece scratch sized for the worst case up front, so the
+// whole pipeline is enqueued without a host round trip in the middle.
+static const uint64_t PRESIZE_LIMIT = 256ull << 20;
+
+static int run_pipeline(b200bpe *h, Slot &S, const uint8_t *d_text, uint64_t n_bytes, const unsigned long long *d_doc_off,
                         uint64_t n_docs, uint32_t *d_out, unsigned long long *d_tok_off, cudaStream_t st,
-                        bool single_piece) {
+                        bool single_piece, bool defer_finish = false) {
     if (n_bytes >= (1ull << 32) - 4096) return fail(B200BPE_EINVAL, "batch too large for one call (>= 4 GiB)");
     if (n_docs >= 0xFFFFFFFEull) return fail(B200BPE_EINVAL, "too many documents in one call");
     const long long n_words = (long long)((n_bytes + 1 + 31) / 32);
     const long long n_tiles = (n_words + 31) / 32;                  // 1 KiB sub-tiles, one warp each
-    CUDA_TRY(h->w_dbits.ensure((size_t)n_words + 4));
-    CUDA_TRY(h->w_pbits.ensure((size_t)n_words + 4));
-    CUDA_TRY(h->w_sfd.ensure((size_t)n_words + 4));
-    CUDA_TRY(h->w_sub_base.ensure((size_t)n_tiles + 2));
-    CUDA_TRY(h->w_sub_count.ensure((size_t)n_tiles + 2)); CUDA_TRY(h->w_sub_flags.ensure((size_t)n_tiles + 2));
-    CUDA_TRY(h->w_tbits.ensure((size_t)n_words + 4));
-    CUDA_TRY(h->w_scratch.ensure((size_t)n_tiles * SUB_CAP + 64));
-    CUDA_TRY(h->w_lidx.ensure((size_t)(n_bytes >> 4) + 4));
+    CUDA_TRY(S.w_dbits.ensure((size_t)n_words + 4));
+    CUDA_TRY(S.w_pbits.ensure((size_t)n_words + 4));
+    CUDA_TRY(S.w_sfd.ensure((size_t)n_words + 4));
+    CUDA_TRY(S.w_sub_base.ensure((size_t)n_tiles + 2));
+    CUDA_TRY(S.w_sub_count.ensure((size_t)n_tiles + 2)); CUDA_TRY(S.w_sub_flags.ensure((size_t)n_tiles + 2));
+    CUDA_TRY(S.w_tbits.ensure((size_t)n_words + 4));
+    CUDA_TRY(S.w_scratch.ensure((size_t)n_tiles * SUB_CAP + 64));
+    CUDA_TRY(S.w_lidx.ensure((size_t)(n_bytes >> 4) + 4));
     const size_t qcap = (size_t)(n_bytes / (SHORT_MAX + 1)) + 4;
-    CUDA_TRY(h->w_lq_start.ensure(qcap)); CUDA_TRY(h->w_lq_off.ensure(qcap));
-    CUDA_TRY(h->w_lq_len.ensure(qcap)); CUDA_TRY(h->w_lq_ntok.ensure(qcap));
-    LongQ q{h->w_lq_start.p, h->w_lq_len.p, h->w_lq_off.p, h->w_lq_ntok.p};
+    CUDA_TRY(S.w_lq_start.ensure(qcap)); CUDA_TRY(S.w_lq_off.ensure(qcap));
+    CUDA_TRY(S.w_lq_len.ensure(qcap)); CUDA_TRY(S.w_lq_ntok.ensure(qcap));
+    LongQ q{S.w_lq_start.p, S.w_lq_len.p, S.w_lq_off.p, S.w_lq_ntok.p};
     uint32_t launches = 0;
 
-    CUDA_TRY(cudaEventRecord(h->ev[0], st));
-    CUDA_TRY(cudaMemsetAsync(h->d_ctr, 0, sizeof(Counters), st));
-    CUDA_TRY(cudaMemsetAsync(h->w_dbits.p, 0, ((size_t)n_words + 4) * 4, st));
-    CUDA_TRY(cudaMemsetAsync(h->w_sfd.p, 0xFF, ((size_t)n_words + 4) * 4, st));
-    CUDA_TRY(cudaMemsetAsync(h->w_pbits.p + n_words, 0, 4 * 4, st));
+    CUDA_TRY(cudaEventRecord(S.ev[0], st));
+    CUDA_TRY(cudaMemsetAsync(S.d_ctr, 0, sizeof(Counters), st));
+    CUDA_TRY(cudaMemsetAsync(S.w_dbits.p, 0, ((size_t)n_words + 4) * 4, st));
+    CUDA_TRY(cudaMemsetAsync(S.w_sfd.p, 0xFF, ((size_t)n_words + 4) * 4, st));
+    CUDA_TRY(cudaMemsetAsync(S.w_pbits.p + n_words, 0, 4 * 4, st));
     {
         unsigned long long nd1 = n_docs + 1;
-        mark_docs_kernel<<<(unsigned)((nd1 + 255) / 256), 256, 0, st>>>(d_doc_off, n_docs, n_bytes, h->w_dbits.p,
-                                                                       h->w_sfd.p, h->d_ctr);
+        mark_docs_kernel<<<(unsigned)((nd1 + 255) / 256), 256, 0, st>>>(d_doc_off, n_docs, n_bytes, S.w_dbits.p,
+                                                                       S.w_sfd.p, S.d_ctr);
         launches++;
     }
-    CUDA_TRY(cudaEventRecord(h->ev[1], st));
+    CUDA_TRY(cudaEventRecord(S.ev[1], st));
     {
         unsigned grid = (unsigned)((n_words + 255) / 256);
-        if (single_piece) single_piece_bits_kernel<<<grid, 256, 0, st>>>(h->w_pbits.p, (long long)n_bytes, n_words);
+        if (single_piece) single_piece_bits_kernel<<<grid, 256, 0, st>>>(S.w_pbits.p, (long long)n_bytes, n_words);
         else if (h->pattern == PAT_R50K)
-            pretok_kernel<PAT_R50K><<<grid, 256, 0, st>>>(d_text, (long long)n_bytes, h->w_dbits.p, h->uc, h->w_pbits.p, n_words);
+            pretok_kernel<PAT_R50K><<<grid, 256, 0, st>>>(d_text, (long long)n_bytes, S.w_dbits.p, h->uc, S.w_pbits.p, n_words);
         else if (h->pattern == PAT_CL100K)
-            pretok_kernel<PAT_CL100K><<<grid, 256, 0, st>>>(d_text, (long long)n_bytes, h->w_dbits.p, h->uc, h->w_pbits.p, n_words);
+            pretok_kernel<PAT_CL100K><<<grid, 256, 0, st>>>(d_text, (long long)n_bytes, S.w_dbits.p, h->uc, S.w_pbits.p, n_words);
         else
-            pretok_kernel<PAT_O200K><<<grid, 256, 0, st>>>(d_text, (long long)n_bytes, h->w_dbits.p, h->uc, h->w_pbits.p, n_words);
+            pretok_kernel<PAT_O200K><<<grid, 256, 0, st>>>(d_text, (long long)n_bytes, S.w_dbits.p, h->uc, S.w_pbits.p, n_words);
         launches++;
     }
-    CUDA_TRY(cudaEventRecord(h->ev[2], st));
+    CUDA_TRY(cudaEventRecord(S.ev[2], st));
     {
         unsigned grid = (unsigned)((n_words + 255) / 256);
-        find_long_kernel<<<grid, 256, 0, st>>>(h->w_pbits.p, (long long)n_bytes, n_words, q, h->w_lidx.p, h->d_ctr);
+        find_long_kernel<<<grid, 256, 0, st>>>(S.w_pbits.p, (long long)n_bytes, n_words, q, S.w_lidx.p, S.d_ctr);
         launches++;
     }
-    CUDA_TRY(cudaMemcpyAsync(h->h_ctr, h->d_ctr, sizeof(Counters), cudaMemcpyDeviceToHost, st));
-    CUDA_TRY(cudaStreamSynchronize(st));
-    if (h->h_ctr->err & ERR_DOCOFF) return fail(B200BPE_EINVAL, "document offsets must start at 0, be non-decreasing and end at n_bytes");
-    const unsigned int n_long = h->h_ctr->n_long;
-    const size_t long_bytes = (size_t)h->h_ctr->long_bytes;
-    if (n_long) {
-        CUDA_TRY(h->w_ltok.ensure(long_bytes + 4));
-        CUDA_TRY(h->w_idA.ensure(long_bytes + 4)); CUDA_TRY(h->w_rkA.ensure(long_bytes + 4));
-        CUDA_TRY(h->w_idB.ensure(long_bytes + 4)); CUDA_TRY(h->w_rkB.ensure(long_bytes + 4));
-        CUDA_TRY(h->w_aux1.ensure(long_bytes + 4)); CUDA_TRY(h->w_aux2.ensure(long_bytes + 4));
-        CUDA_TRY(h->w_flag.ensure(long_bytes + 4));
-        LongScratch S{h->w_idA.p, h->w_rkA.p, h->w_idB.p, h->w_rkB.p, h->w_aux1.p, h->w_aux2.p, h->w_flag.p};
-        unsigned warps = n_long;
-        unsigned blocks = (warps + 7) / 8;
-        if (blocks > 148 * 8) blocks = 148 * 8;
-        long_piece_kernel<<<blocks, 256, 0, st>>>(d_text, h->T, q, S, h->w_ltok.p, h->d_ctr);
-        launches++;
-    } else {
-        CUDA_TRY(h->w_ltok.ensure(4));
+    const bool presized = n_bytes <= PRESIZE_LIMIT;
+    size_t long_cap = (size_t)n_bytes + 4;
+    unsigned long_blocks = 148 * 4;
+    if (!presized) {
+        CUDA_TRY(cudaMemcpyAsync(S.h_ctr, S.d_ctr, sizeof(Counters), cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+        if (S.h_ctr->err & ERR_DOCOFF) return fail(B200BPE_EINVAL, "document offsets must start at 0, be non-decreasing and end at n_bytes");
+        long_cap = (size_t)S.h_ctr->long_bytes + 4;
+        long_blocks = (S.h_ctr->n_long + 7) / 8;
+        if (long_blocks > 148 * 8) long_blocks = 148 * 8;
     }
-    CUDA_TRY(cudaEventRecord(h->ev[3], st));
+    CUDA_TRY(S.w_ltok.ensure(long_cap));
+    if (long_blocks) {
+        CUDA_TRY(S.w_idA.ensure(long_cap)); CUDA_TRY(S.w_rkA.ensure(long_cap));
+        CUDA_TRY(S.w_idB.ensure(long_cap)); CUDA_TRY(S.w_rkB.ensure(long_cap));
+        CUDA_TRY(S.w_aux1.ensure(long_cap)); CUDA_TRY(S.w_aux2.ensure(long_cap));
+        CUDA_TRY(S.w_flag.ensure(long_cap));
+        LongScratch LS{S.w_idA.p, S.w_rkA.p, S.w_idB.p, S.w_rkB.p, S.w_aux1.p, S.w_aux2.p, S.w_flag.p};
+        long_piece_kernel<<<long_blocks, 256, 0, st>>>(d_text, h->T, q, LS, S.w_ltok.p, S.d_ctr);
+        launches++;
+    }
+    CUDA_TRY(cudaEventRecord(S.ev[3], st));
     {
         TileParams p;
         p.text = d_text; p.n_bytes = (long long)n_bytes; p.n_words = n_words; p.n_sub = n_tiles;
-        p.pbits = h->w_pbits.p; p.dbits = h->w_dbits.p; p.span_first_doc = h->w_sfd.p;
-        p.doc_off = d_doc_off; p.n_docs = n_docs; p.q = q; p.lidx = h->w_lidx.p; p.ltok = h->w_ltok.p;
-        p.scratch = h->w_scratch.p; p.tbits = h->w_tbits.p; p.sub_count = h->w_sub_count.p;
-        p.sub_flags = h->w_sub_flags.p; p.sub_base = h->w_sub_base.p;
-        p.out = d_out; p.tok_off = d_tok_off; p.ctr = h->d_ctr;
+        p.pbits = S.w_pbits.p; p.dbits = S.w_dbits.p; p.span_first_doc = S.w_sfd.p;
+        p.doc_off = d_doc_off; p.n_docs = n_docs; p.q = q; p.lidx = S.w_lidx.p; p.ltok = S.w_ltok.p;
+        p.scratch = S.w_scratch.p; p.tbits = S.w_tbits.p; p.sub_count = S.w_sub_count.p;
+        p.sub_flags = S.w_sub_flags.p; p.sub_base = S.w_sub_base.p;
+        p.out = d_out; p.tok_off = d_tok_off; p.ctr = S.d_ctr;
         encode_tiles_kernel<<<(unsigned)((n_tiles + ENC_WARPS - 1) / ENC_WARPS), ENC_WARPS * 32, 0, st>>>(p, h->T);
-        CUDA_TRY(cudaEventRecord(h->ev[7], st));
-        scan_counts_kernel<<<1, 1024, 0, st>>>(h->w_sub_count.p, n_tiles, h->w_sub_base.p);
+        CUDA_TRY(cudaEventRecord(S.ev[7], st));
+        scan_counts_kernel<<<1, 1024, 0, st>>>(S.w_sub_count.p, n_tiles, S.w_sub_base.p, S.d_ctr);
         gather_kernel<<<(unsigned)((n_tiles + 7) / 8), 256, 0, st>>>(p);
         launches += 3;
     }
-    CUDA_TRY(cudaEventRecord(h->ev[4], st));
-    CUDA_TRY(cudaMemcpyAsync(h->h_ctr, h->d_ctr, sizeof(Counters), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaEventRecord(S.ev[4], st));
+    CUDA_TRY(cudaMemcpyAsync(S.h_ctr, S.d_ctr, sizeof(Counters), cudaMemcpyDeviceToHost, st));
+    S.last_launches = launches;
+    if (defer_finish) return B200BPE_OK;
+    return finish_pipeline(h, S, st);
+}
+
+// wait for an enqueued pipeline, collect stage timings and device-side error flags
+static int finish_pipeline(b200bpe *h, Slot &S, cudaStream_t st) {
+    (void)h;
     CUDA_TRY(cudaStreamSynchronize(st));
     CUDA_TRY(cudaGetLastError());
-    cudaEventElapsedTime(&h->last_ms[0], h->ev[0], h->ev[1]);
-    cudaEventElapsedTime(&h->last_ms[1], h->ev[1], h->ev[2]);
-    cudaEventElapsedTime(&h->last_ms[2], h->ev[2], h->ev[3]);
-    cudaEventElapsedTime(&h->last_ms[3], h->ev[3], h->ev[7]);
-    cudaEventElapsedTime(&h->last_ms[7], h->ev[7], h->ev[4]);
-    cudaEventElapsedTime(&h->last_ms[4], h->ev[0], h->ev[4]);
-    h->last_launches = launches;
-    if (h->h_ctr->err & ERR_NOBYTE)
+    cudaEventElapsedTime(&S.last_ms[0], S.ev[0], S.ev[1]);
+    cudaEventElapsedTime(&S.last_ms[1], S.ev[1], S.ev[2]);
+    cudaEventElapsedTime(&S.last_ms[2], S.ev[2], S.ev[3]);
+    cudaEventElapsedTime(&S.last_ms[3], S.ev[3], S.ev[7]);
+    cudaEventElapsedTime(&S.last_ms[7], S.ev[7], S.ev[4]);
+    cudaEventElapsedTime(&S.last_ms[4], S.ev[0], S.ev[4]);
+    if (S.h_ctr->err & ERR_DOCOFF)
+        return fail(B200BPE_EINVAL, "document offsets must start at 0, be non-decreasing and end at n_bytes");
+    if (S.h_ctr->err & ERR_NOBYTE)
         return fail(B200BPE_ENOBYTE, "a piece needs a single-byte token that mergeable_ranks does not contain");
     return B200BPE_OK;
 }
@@ -878,58 +923,127 @@ extern "C" int b200bpe_encode_device(b200bpe_t *h, const uint8_t *d_text, uint64
     if (!h || !d_doc_off || !d_tokens || !d_tok_off || (n_bytes && !d_text)) return fail(B200BPE_EINVAL, "null argument");
     std::lock_guard<std::mutex> lk(h->mu);
     CUDA_TRY(cudaSetDevice(h->device));
-    cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
+    Slot &S = h->slots[0];
+    cudaStream_t st = stream ? (cudaStream_t)stream : S.stream;
     const uint8_t *txt = d_text;
     if (((uintptr_t)d_text & 15u) != 0) {                       // vector loads need 16-byte alignment
-        CUDA_TRY(h->w_text.ensure((size_t)n_bytes + 64));
-        CUDA_TRY(cudaMemcpyAsync(h->w_text.p, d_text, n_bytes, cudaMemcpyDeviceToDevice, st));
-        txt = h->w_text.p;
+        CUDA_TRY(S.w_text.ensure((size_t)n_bytes + 64));
+        CUDA_TRY(cudaMemcpyAsync(S.w_text.p, d_text, n_bytes, cudaMemcpyDeviceToDevice, st));
+        txt = S.w_text.p;
     }
-    h->last_ms[5] = h->last_ms[6] = 0.f;
-    int rc = run_pipeline(h, txt, n_bytes, (const unsigned long long *)d_doc_off, n_docs, d_tokens,
+    int rc = run_pipeline(h, S, txt, n_bytes, (const unsigned long long *)d_doc_off, n_docs, d_tokens,
                           (unsigned long long *)d_tok_off, st, false);
+    memcpy(h->last_ms, S.last_ms, sizeof(h->last_ms));
+    h->last_ms[5] = h->last_ms[6] = 0.f;
+    h->last_launches = S.last_launches;
     if (rc) return rc;
-    if (n_tokens) {
-        unsigned long long total = 0;
-        CUDA_TRY(cudaMemcpyAsync(&total, (unsigned long long *)d_tok_off + n_docs, 8, cudaMemcpyDeviceToHost, st));
-        CUDA_TRY(cudaStreamSynchronize(st));
-        *n_tokens = total;
-    }
+    if (n_tokens) *n_tokens = S.h_ctr->total_tokens;
     return B200BPE_OK;
 }
 
-// host buffers in, pinned host buffers out
+// Host buffers in, pinned host buffers out.  Large batches are cut at document boundaries into
+// chunks of ~chunk_bytes and pipelined over three slots: while chunk c is in the kernels, chunk
+// c+1 is already crossing PCIe host->device and the tokens of chunk c-1 are crossing device->host.
 static int encode_host(b200bpe *h, const uint8_t *text, const uint64_t *doc_off, uint64_t n_docs, bool single_piece,
                        b200bpe_result **out) {
     const uint64_t n_bytes = doc_off[n_docs];
     CUDA_TRY(cudaSetDevice(h->device));
-    cudaStream_t st = h->stream;
-    CUDA_TRY(h->w_text.ensure((size_t)n_bytes + 64));
-    CUDA_TRY(h->w_docoff.ensure((size_t)n_docs + 2));
-    CUDA_TRY(h->w_tokoff.ensure((size_t)n_docs + 2));
-    CUDA_TRY(h->w_out.ensure((size_t)n_bytes + 64));
-    CUDA_TRY(cudaEventRecord(h->ev[5], st));
-    if (n_bytes) CUDA_TRY(cudaMemcpyAsync(h->w_text.p, text, n_bytes, cudaMemcpyHostToDevice, st));
-    CUDA_TRY(cudaMemcpyAsync(h->w_docoff.p, doc_off, (n_docs + 1) * 8, cudaMemcpyHostToDevice, st));
-    CUDA_TRY(cudaEventRecord(h->ev[6], st));
-    int rc = run_pipeline(h, h->w_text.p, n_bytes, h->w_docoff.p, n_docs, h->w_out.p, h->w_tokoff.p, st, single_piece);
-    if (rc) return rc;
-    float h2d = 0; cudaEventElapsedTime(&h2d, h->ev[5], h->ev[6]);
+    if (doc_off[0] != 0) return fail(B200BPE_EINVAL, "document offsets must start at 0");
+    // ---- chunk plan: document ranges [lo, hi) ------------------------------------------------
+    std::vector<uint64_t> cut; cut.push_back(0);
+    if (!single_piece && n_bytes > h->chunk_bytes + h->chunk_bytes / 2) {
+        uint64_t lo = 0;
+        while (lo < n_docs) {
+            const uint64_t want = doc_off[lo] + h->chunk_bytes;
+            uint64_t hi = (uint64_t)(std::upper_bound(doc_off + lo, doc_off + n_docs + 1, want) - doc_off);   // first off > want
+            if (hi > 0) hi--;                                    // last doc boundary <= want
+            if (hi <= lo) hi = lo + 1;                           // a single document larger than a chunk
+            if (hi > n_docs) hi = n_docs;
+            cut.push_back(hi); lo = hi;
+        }
+    } else cut.push_back(n_docs);
+    const size_t n_chunks = cut.size() - 1;
+    for (size_t c = 0; c < n_chunks; c++) {
+        const uint64_t cb = doc_off[cut[c + 1]] - doc_off[cut[c]];
+        if (doc_off[cut[c + 1]] < doc_off[cut[c]] || cb >= (1ull << 32) - 4096)
+            return fail(B200BPE_EINVAL, cb >= (1ull << 32) - 4096 ? "a single document of >= 4 GiB is not supported"
+                                                                  : "document offsets must be non-decreasing");
+    }
     b200bpe_result *r = new b200bpe_result();
     r->owner = h; r->n_docs = n_docs;
     r->off = h->take_pinned((size_t)(n_docs + 1) * 8);
-    if (!r->off.p) { delete r; return fail(B200BPE_ECUDA, "pinned allocation failed"); }
-    CUDA_TRY(cudaEventRecord(h->ev[5], st));
-    CUDA_TRY(cudaMemcpyAsync(r->off.p, h->w_tokoff.p, (n_docs + 1) * 8, cudaMemcpyDeviceToHost, st));
-    CUDA_TRY(cudaStreamSynchronize(st));
-    r->n_tokens = ((uint64_t *)r->off.p)[n_docs];
-    r->tok = h->take_pinned((size_t)r->n_tokens * 4 + 16);
-    if (!r->tok.p) { h->give_pinned(r->off); delete r; return fail(B200BPE_ECUDA, "pinned allocation failed"); }
-    if (r->n_tokens) CUDA_TRY(cudaMemcpyAsync(r->tok.p, h->w_out.p, r->n_tokens * 4, cudaMemcpyDeviceToHost, st));
-    CUDA_TRY(cudaEventRecord(h->ev[6], st));
-    CUDA_TRY(cudaStreamSynchronize(st));
-    float d2h = 0; cudaEventElapsedTime(&d2h, h->ev[5], h->ev[6]);
-    h->last_ms[5] = h2d; h->last_ms[6] = d2h;
+    size_t tok_cap = (size_t)(n_bytes / 3) + 4096;               // tokens <= bytes; typical bytes/4; grows if needed
+    r->tok = h->take_pinned(tok_cap * 4);
+    auto cleanup = [&](int rc) { h->give_pinned(r->tok); h->give_pinned(r->off); delete r; return rc; };
+    if (!r->off.p || !r->tok.p) return cleanup(fail(B200BPE_ECUDA, "pinned allocation failed"));
+    tok_cap = r->tok.cap / 4;
+
+    auto enqueue_h2d = [&](size_t c) -> int {
+        Slot &S = h->slots[c % b200bpe::N_SLOTS];
+        CUDA_TRY(cudaStreamSynchronize(S.stream));               // slot free again (its chunk c-3 fully drained)
+        const uint64_t lo = cut[c], hi = cut[c + 1], b0 = doc_off[lo], nb = doc_off[hi] - b0, nd = hi - lo;
+        CUDA_TRY(S.w_text.ensure((size_t)nb + 64)); CUDA_TRY(S.w_docoff.ensure((size_t)nd + 2));
+        CUDA_TRY(S.w_tokoff.ensure((size_t)nd + 2)); CUDA_TRY(S.w_out.ensure((size_t)nb + 64));
+        CUDA_TRY(cudaEventRecord(S.ev[5], S.stream));
+        if (nb) CUDA_TRY(cudaMemcpyAsync(S.w_text.p, text + b0, nb, cudaMemcpyHostToDevice, S.stream));
+        CUDA_TRY(cudaMemcpyAsync(S.w_docoff.p, doc_off + lo, (nd + 1) * 8, cudaMemcpyHostToDevice, S.stream));
+        if (b0) add_offset_kernel<<<(unsigned)((nd + 1 + 255) / 256), 256, 0, S.stream>>>(S.w_docoff.p, nd + 1, -(long long)b0);
+        CUDA_TRY(cudaEventRecord(S.ev[6], S.stream));
+        return B200BPE_OK;
+    };
+
+    float sum_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0}; uint32_t launches = 0;
+    uint64_t token_base = 0;
+    // finalise chunk c: wait for its kernels, then send its offsets + tokens home (async)
+    auto drain = [&](size_t c) -> int {
+        Slot &S = h->slots[c % b200bpe::N_SLOTS];
+        const uint64_t lo = cut[c], hi = cut[c + 1], nd = hi - lo;
+        int rc2 = finish_pipeline(h, S, S.stream);
+        if (rc2) return rc2;
+        float h2d = 0; cudaEventElapsedTime(&h2d, S.ev[5], S.ev[6]);
+        const uint64_t nt = S.h_ctr->total_tokens;
+        if (token_base + nt > tok_cap) {                         // rare: grow the pinned token buffer
+            for (int i = 0; i < b200bpe::N_SLOTS; i++) CUDA_TRY(cudaStreamSynchronize(h->slots[i].stream));
+            size_t want = (size_t)((token_base + nt) * 1.5) + 4096;
+            PinnedBuf nbuf = h->take_pinned(want * 4);
+            if (!nbuf.p) return fail(B200BPE_ECUDA, "pinned allocation failed");
+            memcpy(nbuf.p, r->tok.p, (size_t)token_base * 4);
+            h->give_pinned(r->tok); r->tok = nbuf; tok_cap = nbuf.cap / 4;
+        }
+        if (token_base) add_offset_kernel<<<(unsigned)((nd + 1 + 255) / 256), 256, 0, S.stream>>>(S.w_tokoff.p, nd + 1, (long long)token_base);
+        CUDA_TRY(cudaEventRecord(S.ev[5], S.stream));
+        CUDA_TRY(cudaMemcpyAsync((uint64_t *)r->off.p + lo, S.w_tokoff.p, (nd + 1) * 8, cudaMemcpyDeviceToHost, S.stream));
+        if (nt) CUDA_TRY(cudaMemcpyAsync((uint32_t *)r->tok.p + token_base, S.w_out.p, nt * 4, cudaMemcpyDeviceToHost, S.stream));
+        CUDA_TRY(cudaEventRecord(S.ev[6], S.stream));
+        token_base += nt;
+        for (int i = 0; i < 5; i++) sum_ms[i] += S.last_ms[i];
+        sum_ms[7] += S.last_ms[7]; sum_ms[5] += h2d; launches += S.last_launches;
+        return B200BPE_OK;
+    };
+    auto fail_all = [&](int rc2) {
+        for (int i = 0; i < b200bpe::N_SLOTS; i++) cudaStreamSynchronize(h->slots[i].stream);
+        return cleanup(rc2);
+    };
+    int rc = enqueue_h2d(0);
+    if (rc) return fail_all(rc);
+    for (size_t c = 0; c < n_chunks; c++) {
+        // slot (c+1)%3 last served chunk c-2, which was drained in the previous iteration
+        if (c + 1 < n_chunks) { rc = enqueue_h2d(c + 1); if (rc) return fail_all(rc); }
+        Slot &S = h->slots[c % b200bpe::N_SLOTS];
+        const uint64_t lo = cut[c], hi = cut[c + 1], nb = doc_off[hi] - doc_off[lo], nd = hi - lo;
+        rc = run_pipeline(h, S, S.w_text.p, nb, S.w_docoff.p, nd, S.w_out.p, S.w_tokoff.p, S.stream, single_piece, true);
+        if (rc) return fail_all(rc);
+        if (c >= 1) { rc = drain(c - 1); if (rc) return fail_all(rc); }   // overlaps with chunk c's kernels
+    }
+    rc = drain(n_chunks - 1);
+    if (rc) return fail_all(rc);
+    for (int i = 0; i < b200bpe::N_SLOTS; i++) CUDA_TRY(cudaStreamSynchronize(h->slots[i].stream));
+    {   // D2H time of the last chunk only (the others overlap with later chunks' kernels)
+        Slot &S = h->slots[(n_chunks - 1) % b200bpe::N_SLOTS];
+        float d2h = 0; cudaEventElapsedTime(&d2h, S.ev[5], S.ev[6]); sum_ms[6] = d2h;
+    }
+    memcpy(h->last_ms, sum_ms, sizeof(sum_ms)); h->last_launches = launches;
+    r->n_tokens = token_base;
     *out = r;
     return B200BPE_OK;
 }
