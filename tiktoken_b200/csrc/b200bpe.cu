@@ -56,6 +56,7 @@ struct Counters {            // device-resident, zeroed per call
     unsigned long long long_bytes;
     unsigned int n_long;
     unsigned int long_head;
+    unsigned int giant_head;
     unsigned int ticket;
     unsigned int err;
     unsigned long long total_tokens;
@@ -153,6 +154,8 @@ __global__ void __launch_bounds__(256) find_long_kernel(const uint32_t *__restri
 // State lives in global scratch (L2 resident): parts as dense arrays id[], rk[] (rank of the pair
 // starting at that part), double buffered for the per-round compaction.
 // --------------------------------------------------------------------------------------------
+static const uint32_t GIANT_MIN = 4096;      // pieces longer than this get a whole block (kernel 3b)
+
 struct LongScratch {
     uint32_t *idA, *rkA, *idB, *rkB, *aux1, *aux2;
     uint8_t *flag;
@@ -230,11 +233,14 @@ __device__ uint32_t long_piece_warp(const DevTables &T, const uint8_t *__restric
         for (uint32_t i = lane; i < m; i += 32) {
             if (!S.flag[i]) continue;
             uint32_t nl = RANK_MAX, nr = RANK_MAX;
-            if (i >= 1) {
-                uint32_t lid = (i >= 2 && S.flag[i - 2]) ? g : id[i - 1];
-                nl = pair_lookup(T, lid, g);
+            if (i >= 1 && i + 2 < m) {                      // both neighbour probes in flight together
+                const uint32_t lid = (i >= 2 && S.flag[i - 2]) ? g : id[i - 1];
+                pair_lookup2(T, lid, g, g, id[i + 2], nl, nr);
+            } else if (i >= 1) {
+                nl = pair_lookup(T, (i >= 2 && S.flag[i - 2]) ? g : id[i - 1], g);
+            } else if (i + 2 < m) {
+                nr = pair_lookup(T, g, id[i + 2]);
             }
-            if (i + 2 < m) nr = pair_lookup(T, g, id[i + 2]);
             S.aux1[i] = nl; S.aux2[i] = nr;
             if (nl < g || nr < g) vmin = min(vmin, i);
         }
@@ -280,21 +286,201 @@ __device__ uint32_t long_piece_warp(const DevTables &T, const uint8_t *__restric
     return m;
 }
 
-__global__ void __launch_bounds__(256) long_piece_kernel(const uint8_t *__restrict__ text, DevTables T, LongQ q,
-                                                         LongScratch S, uint32_t *ltok, Counters *ctr) {
-    const int lane = threadIdx.x & 31;
+static const int LONG_WARPS = 4;               // warps per block of long_piece_kernel
+static const uint32_t LONG_SMEM_MAX = 256;      // pieces up to this many bytes keep their merge state in shared memory
+
+__global__ void __launch_bounds__(LONG_WARPS * 32) long_piece_kernel(const uint8_t *__restrict__ text, DevTables T, LongQ q,
+                                                                    LongScratch S, uint32_t *ltok, Counters *ctr) {
+    // per-warp merge state for mid-size pieces (CJK runs, indentation, separators): 25 B per byte
+    __shared__ uint32_t s_u32[LONG_WARPS][6][LONG_SMEM_MAX];
+    __shared__ uint8_t s_u8[LONG_WARPS][LONG_SMEM_MAX];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const unsigned int n_long = ctr->n_long;
     for (;;) {
         unsigned int i = 0;
         if (lane == 0) i = atomicAdd(&ctr->long_head, 1u);
         i = __shfl_sync(0xFFFFFFFFu, i, 0);
         if (i >= n_long) break;
+        const uint32_t len = q.len[i];
+        if (len > GIANT_MIN) continue;                          // handled by giant_piece_kernel (whole block)
         unsigned long long off = q.off[i];
-        LongScratch P = S;
-        P.idA += off; P.rkA += off; P.idB += off; P.rkB += off; P.aux1 += off; P.aux2 += off; P.flag += off;
-        uint32_t nt = long_piece_warp(T, text + q.start[i], q.len[i], P, ltok + off, &ctr->err);
+        LongScratch P;
+        if (len <= LONG_SMEM_MAX) {
+            P.idA = s_u32[wid][0]; P.rkA = s_u32[wid][1]; P.idB = s_u32[wid][2]; P.rkB = s_u32[wid][3];
+            P.aux1 = s_u32[wid][4]; P.aux2 = s_u32[wid][5]; P.flag = s_u8[wid];
+        } else {
+            P = S;
+            P.idA += off; P.rkA += off; P.idB += off; P.rkB += off; P.aux1 += off; P.aux2 += off; P.flag += off;
+        }
+        uint32_t nt = long_piece_warp(T, text + q.start[i], len, P, ltok + off, &ctr->err);
         if (lane == 0) q.ntok[i] = nt;
         __syncwarp();
+    }
+}
+
+// --------------------------------------------------------------------------------------------
+// kernel 3b: giant pieces (> GIANT_MIN bytes: "x"*1_000_000, long whitespace / separator runs).
+// Same round-synchronous algorithm as long_piece_warp, executed by a whole 1024-thread block:
+// every phase walks the parts in tiles of 1024 with warp ballots and a small cross-warp carry.
+// --------------------------------------------------------------------------------------------
+static const int GIANT_THREADS = 1024;
+
+__device__ __forceinline__ uint32_t block_min_u32(uint32_t v, uint32_t *s_red) {
+    v = warp_min_u32(v);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    uint32_t r = s_red[threadIdx.x & 31];
+    r = warp_min_u32(r);
+    return r;
+}
+
+__device__ uint32_t long_piece_block(const DevTables &T, const uint8_t *__restrict__ piece, uint32_t n,
+                                     LongScratch S, uint32_t *__restrict__ out, uint32_t *err) {
+    __shared__ uint32_t s_red[32];
+    __shared__ uint32_t s_wmask[32];     // per-warp candidate / survivor ballots of the current tile
+    __shared__ uint32_t s_carry;         // parity carry (select) or running output offset (compaction)
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    if (n <= T.max_token_len) {          // whole-piece probe (only a token of that length could match)
+        uint32_t r = RANK_MAX;
+        if (tid == 0) {
+            uint64_t h = long_hash_init(n);
+            for (uint32_t i = 0; i < n; i += 8) {
+                uint64_t w = 0;
+                for (uint32_t k = 0; k < 8 && i + k < n; k++) w |= (uint64_t)piece[i + k] << (8 * k);
+                h = long_hash_step(h, w);
+            }
+            r = piece_lookup_long(T, h, n, [&](uint32_t i) { return piece[i]; });
+            s_red[0] = r;
+        }
+        __syncthreads();
+        r = s_red[0];
+        __syncthreads();
+        if (r != RANK_MAX) { if (tid == 0) out[0] = r; return 1; }
+    }
+    uint32_t *id = S.idA, *rk = S.rkA, *id2 = S.idB, *rk2 = S.rkB;
+    for (uint32_t i = tid; i < n; i += GIANT_THREADS) {
+        uint32_t b = piece[i];
+        id[i] = __ldg(T.byte_id + b);
+        rk[i] = (i + 1 < n) ? __ldg(T.pair2 + ((b << 8) | piece[i + 1])) : RANK_MAX;
+    }
+    __syncthreads();
+    uint32_t m = n;
+    for (;;) {
+        // A. global minimum rank
+        uint32_t g = RANK_MAX;
+        for (uint32_t i = tid; i < m; i += GIANT_THREADS) g = min(g, rk[i]);
+        g = block_min_u32(g, s_red);
+        if (g == RANK_MAX) break;
+        // B. select alternate members of every chain of consecutive candidates
+        if (tid == 0) s_carry = 0;
+        __syncthreads();
+        for (uint32_t base = 0; base < m; base += GIANT_THREADS) {
+            const uint32_t i = base + tid;
+            const bool cand = i < m && rk[i] == g;
+            const uint32_t c = __ballot_sync(0xFFFFFFFFu, cand);
+            if (lane == 0) s_wmask[wid] = c;
+            __syncthreads();
+            // parity of the candidate run that ends right before this warp's first lane
+            uint32_t par = 0; bool open = true;
+            for (int w = wid - 1; w >= 0 && open; w--) {
+                const uint32_t cw = s_wmask[w];
+                if (cw == 0xFFFFFFFFu) continue;               // 32 more candidates: parity unchanged
+                par = (uint32_t)__clz((int)~cw) & 1u; open = false;
+            }
+            if (open) par = s_carry;                            // run reaches back into the previous tile
+            const uint32_t zeros_below = ~c & ((1u << lane) - 1u);
+            uint32_t before;
+            if (zeros_below == 0) before = (uint32_t)lane + par;
+            else before = (uint32_t)lane - (32u - (uint32_t)__clz((int)zeros_below));
+            if (i < m) S.flag[i] = (cand && ((before & 1u) == 0)) ? 1 : 0;
+            __syncthreads();
+            if (tid == GIANT_THREADS - 1) {                     // carry for the next tile
+                uint32_t par2 = s_carry; bool open2 = true;
+                for (int w = 31; w >= 0 && open2; w--) {
+                    const uint32_t cw = s_wmask[w];
+                    if (cw == 0xFFFFFFFFu) continue;
+                    par2 = (uint32_t)__clz((int)~cw) & 1u; open2 = false;
+                }
+                s_carry = par2;
+            }
+            __syncthreads();
+        }
+        // C. new neighbour ranks of the selected merges, first violation
+        uint32_t vmin = RANK_MAX;
+        for (uint32_t i = tid; i < m; i += GIANT_THREADS) {
+            if (!S.flag[i]) continue;
+            uint32_t nl = RANK_MAX, nr = RANK_MAX;
+            if (i >= 1) nl = pair_lookup(T, (i >= 2 && S.flag[i - 2]) ? g : id[i - 1], g);
+            if (i + 2 < m) nr = pair_lookup(T, g, id[i + 2]);
+            S.aux1[i] = nl; S.aux2[i] = nr;
+            if (nl < g || nr < g) vmin = min(vmin, i);
+        }
+        const uint32_t v = block_min_u32(vmin, s_red);
+        __syncthreads();
+        // D. commit merges at positions <= v, compact into the other buffer
+        if (tid == 0) s_carry = 0;
+        __syncthreads();
+        for (uint32_t base = 0; base < m; base += GIANT_THREADS) {
+            const uint32_t i = base + tid;
+            const bool in = i < m;
+            const bool com = in && S.flag[i] && i <= v;
+            const bool absorbed = in && i >= 1 && S.flag[i - 1] && (i - 1) <= v;
+            const bool survive = in && !absorbed;
+            const uint32_t sb = __ballot_sync(0xFFFFFFFFu, survive);
+            if (lane == 0) s_wmask[wid] = (uint32_t)__popc(sb);
+            __syncthreads();
+            uint32_t wbase = s_carry;
+            for (int w = 0; w < wid; w++) wbase += s_wmask[w];
+            if (survive) {
+                uint32_t nid, nrk;
+                if (com) {
+                    nid = g;
+                    const bool com2 = (i + 2 < m) && S.flag[i + 2] && (i + 2) <= v;
+                    nrk = com2 ? S.aux1[i + 2] : S.aux2[i];
+                } else {
+                    nid = id[i];
+                    const bool com1 = (i + 1 < m) && S.flag[i + 1] && (i + 1) <= v;
+                    nrk = com1 ? S.aux1[i + 1] : rk[i];
+                }
+                const uint32_t o = wbase + __popc(sb & ((1u << lane) - 1u));
+                id2[o] = nid; rk2[o] = nrk;
+            }
+            __syncthreads();
+            if (tid == 0) { uint32_t t = s_carry; for (int w = 0; w < 32; w++) t += s_wmask[w]; s_carry = t; }
+            __syncthreads();
+        }
+        m = s_carry;
+        __syncthreads();
+        uint32_t *t1 = id; id = id2; id2 = t1;
+        uint32_t *t2 = rk; rk = rk2; rk2 = t2;
+    }
+    bool bad = false;
+    for (uint32_t i = tid; i < m; i += GIANT_THREADS) {
+        uint32_t x = id[i];
+        out[i] = x;
+        bad |= x >= PSEUDO_BASE;
+    }
+    if (bad) atomicOr(err, ERR_NOBYTE);
+    return m;
+}
+
+__global__ void __launch_bounds__(GIANT_THREADS) giant_piece_kernel(const uint8_t *__restrict__ text, DevTables T, LongQ q,
+                                                                    LongScratch S, uint32_t *ltok, Counters *ctr) {
+    __shared__ unsigned int s_i;
+    const unsigned int n_long = ctr->n_long;
+    for (;;) {
+        __syncthreads();
+        if (threadIdx.x == 0) s_i = atomicAdd(&ctr->giant_head, 1u);
+        __syncthreads();
+        const unsigned int i = s_i;
+        if (i >= n_long) break;
+        if (q.len[i] <= GIANT_MIN) continue;
+        const unsigned long long off = q.off[i];
+        LongScratch P = S;
+        P.idA += off; P.rkA += off; P.idB += off; P.rkB += off; P.aux1 += off; P.aux2 += off; P.flag += off;
+        const uint32_t nt = long_piece_block(T, text + q.start[i], q.len[i], P, ltok + off, &ctr->err);
+        if (threadIdx.x == 0) q.ntok[i] = nt;
     }
 }
 
@@ -405,21 +591,24 @@ __global__ void __launch_bounds__(ENC_WARPS * 32) encode_tiles_kernel(TileParams
     }
     __syncwarp();
 
-    // ---- phase A: whole-piece probe (src/lib.rs:367-368), one piece per lane per iteration -------
+    // ---- phase A: whole-piece probe (src/lib.rs:367-368).  Two pieces per lane per iteration so that
+    //      two table probes are in flight per lane (the loop is bound by L2 latency, not by issue) ----
     uint32_t cl = 0;                                       // tokens of long pieces met by this lane
-    for (uint32_t i = lane; i < np; i += 32) {
-        const int off = S.plist[i];
-        const int len = (int)S.plist[i + 1] - off;
+    auto prep = [&](uint32_t i, int &off, int &len, uint64_t &k0, uint64_t &k1) -> int {
+        // returns 0: nothing to probe (handled here), 1: probe needed
+        if (i >= np) return 0;
+        off = S.plist[i];
+        len = (int)S.plist[i + 1] - off;
         if (len > SHORT_MAX) {                             // long path: precomputed by long_piece_kernel
             atomicAnd(&S.tmask[off >> 5], ~(1u << (off & 31)));
             cl += p.q.ntok[p.lidx[(sub_byte + off) >> 4]];
-            continue;
+            return 0;
         }
         if (len == 1) {
             const uint32_t id = __ldg(T.byte_id + S.text[off]);
             if (id >= PSEUDO_BASE) atomicOr(&p.ctr->err, ERR_NOBYTE);
             S.tok[off] = id;
-            continue;
+            return 0;
         }
         const uint32_t *wp = reinterpret_cast<const uint32_t *>(S.text) + (off >> 2);
         const int sh = (off & 3) * 8;
@@ -429,14 +618,36 @@ __global__ void __launch_bounds__(ENC_WARPS * 32) encode_tiles_kernel(TileParams
         const int nb0 = len >= 8 ? 64 : len * 8, nb1 = len <= 8 ? 0 : (len - 8) * 8;
         const uint64_t mk0 = nb0 >= 64 ? ~0ull : ((1ull << nb0) - 1ull);
         const uint64_t mk1 = nb1 >= 64 ? ~0ull : ((1ull << nb1) - 1ull);
-        const uint64_t k0 = (((uint64_t)a1 << 32) | a0) & mk0, k1 = (((uint64_t)a3 << 32) | a2) & mk1;
-        const uint32_t r = piece_lookup16(T, k0, k1, (uint32_t)len);
+        k0 = (((uint64_t)a1 << 32) | a0) & mk0; k1 = (((uint64_t)a3 << 32) | a2) & mk1;
+        return 1;
+    };
+    auto finish = [&](int off, int len, uint64_t k0, uint64_t k1, uint32_t s, U4 m, U4 k) {
+        uint32_t r = RANK_MAX;
+        for (;;) {                                         // continue the linear probe from the prefetched slot
+            if (m.x == 0) break;
+            if (m.x == (uint32_t)len && k.x == (uint32_t)k0 && k.y == (uint32_t)(k0 >> 32) && k.z == (uint32_t)k1 &&
+                k.w == (uint32_t)(k1 >> 32)) { r = m.y; break; }
+            s = (s + 1) & T.piece_mask;
+            m = B2_LDG_U4(T.piece_tab + 2 * s + 1); k = B2_LDG_U4(T.piece_tab + 2 * s);
+        }
         if (r != RANK_MAX) S.tok[off] = r;
         else {
             atomicAnd(&S.tmask[off >> 5], ~(1u << (off & 31)));
             const uint32_t slot = atomicAdd(&S.nmiss, 1u);
             S.miss[slot] = (uint16_t)(off | ((len - 1) << 12));
         }
+    };
+    for (uint32_t i = lane; i < np; i += 64) {
+        int offA = 0, lenA = 0, offB = 0, lenB = 0;
+        uint64_t a0 = 0, a1 = 0, b0 = 0, b1 = 0;
+        const int needA = prep(i, offA, lenA, a0, a1);
+        const int needB = prep(i + 32, offB, lenB, b0, b1);
+        uint32_t sA = 0, sB = 0;
+        U4 mA = {0, 0, 0, 0}, kA = {0, 0, 0, 0}, mB = {0, 0, 0, 0}, kB = {0, 0, 0, 0};
+        if (needA) { sA = (uint32_t)piece_hash(a0, a1, (uint32_t)lenA) & T.piece_mask; mA = B2_LDG_U4(T.piece_tab + 2 * sA + 1); kA = B2_LDG_U4(T.piece_tab + 2 * sA); }
+        if (needB) { sB = (uint32_t)piece_hash(b0, b1, (uint32_t)lenB) & T.piece_mask; mB = B2_LDG_U4(T.piece_tab + 2 * sB + 1); kB = B2_LDG_U4(T.piece_tab + 2 * sB); }
+        if (needA) finish(offA, lenA, a0, a1, sA, mA, kA);
+        if (needB) finish(offB, lenB, b0, b1, sB, mB, kB);
     }
     __syncwarp();
 
@@ -858,13 +1069,13 @@ static int run_pipeline(b200bpe *h, Slot &S, const uint8_t *d_text, uint64_t n_b
     }
     const bool presized = n_bytes <= PRESIZE_LIMIT;
     size_t long_cap = (size_t)n_bytes + 4;
-    unsigned long_blocks = 148 * 4;
+    unsigned long_blocks = 148 * 8;
     if (!presized) {
         CUDA_TRY(cudaMemcpyAsync(S.h_ctr, S.d_ctr, sizeof(Counters), cudaMemcpyDeviceToHost, st));
         CUDA_TRY(cudaStreamSynchronize(st));
         if (S.h_ctr->err & ERR_DOCOFF) return fail(B200BPE_EINVAL, "document offsets must start at 0, be non-decreasing and end at n_bytes");
         long_cap = (size_t)S.h_ctr->long_bytes + 4;
-        long_blocks = (S.h_ctr->n_long + 7) / 8;
+        long_blocks = (S.h_ctr->n_long + LONG_WARPS - 1) / LONG_WARPS;
         if (long_blocks > 148 * 8) long_blocks = 148 * 8;
     }
     CUDA_TRY(S.w_ltok.ensure(long_cap));
@@ -874,8 +1085,9 @@ static int run_pipeline(b200bpe *h, Slot &S, const uint8_t *d_text, uint64_t n_b
         CUDA_TRY(S.w_aux1.ensure(long_cap)); CUDA_TRY(S.w_aux2.ensure(long_cap));
         CUDA_TRY(S.w_flag.ensure(long_cap));
         LongScratch LS{S.w_idA.p, S.w_rkA.p, S.w_idB.p, S.w_rkB.p, S.w_aux1.p, S.w_aux2.p, S.w_flag.p};
-        long_piece_kernel<<<long_blocks, 256, 0, st>>>(d_text, h->T, q, LS, S.w_ltok.p, S.d_ctr);
-        launches++;
+        long_piece_kernel<<<long_blocks, LONG_WARPS * 32, 0, st>>>(d_text, h->T, q, LS, S.w_ltok.p, S.d_ctr);
+        giant_piece_kernel<<<148, GIANT_THREADS, 0, st>>>(d_text, h->T, q, LS, S.w_ltok.p, S.d_ctr);
+        launches += 2;
     }
     CUDA_TRY(cudaEventRecord(S.ev[3], st));
     {
