@@ -57,16 +57,20 @@ struct Counters {            // device-resident, zeroed per call
     unsigned int n_long;
     unsigned int long_head;
     unsigned int giant_head;
+    unsigned int n_giant;
     unsigned int ticket;
     unsigned int err;
     unsigned long long total_tokens;
 };
+
+static const uint32_t GIANT_MIN = 4096;      // pieces longer than this get a whole block (kernel 3b)
 
 struct LongQ {               // queue of pieces longer than SHORT_MAX bytes
     unsigned long long *start;   // byte offset of the piece
     unsigned int *len;
     unsigned long long *off;     // offset of its region in the long scratch / ltok
     unsigned int *ntok;
+    unsigned int *giant;         // indices (into this queue) of the pieces longer than GIANT_MIN
 };
 
 // --------------------------------------------------------------------------------------------
@@ -137,6 +141,7 @@ __global__ void __launch_bounds__(256) find_long_kernel(const uint32_t *__restri
             unsigned long long off = atomicAdd(&ctr->long_bytes, (unsigned long long)len);
             q.start[i] = (unsigned long long)s; q.len[i] = (unsigned int)len; q.off[i] = off;
             lidx[s >> 4] = i;
+            if (len > GIANT_MIN) q.giant[atomicAdd(&ctr->n_giant, 1u)] = i;
         }
     }
 }
@@ -154,8 +159,6 @@ __global__ void __launch_bounds__(256) find_long_kernel(const uint32_t *__restri
 // State lives in global scratch (L2 resident): parts as dense arrays id[], rk[] (rank of the pair
 // starting at that part), double buffered for the per-round compaction.
 // --------------------------------------------------------------------------------------------
-static const uint32_t GIANT_MIN = 4096;      // pieces longer than this get a whole block (kernel 3b)
-
 struct LongScratch {
     uint32_t *idA, *rkA, *idB, *rkB, *aux1, *aux2;
     uint8_t *flag;
@@ -286,15 +289,129 @@ __device__ uint32_t long_piece_warp(const DevTables &T, const uint8_t *__restric
     return m;
 }
 
-static const int LONG_WARPS = 4;               // warps per block of long_piece_kernel
-static const uint32_t LONG_SMEM_MAX = 256;      // pieces up to this many bytes keep their merge state in shared memory
+// --------------------------------------------------------------------------------------------
+// Mid-size pieces (17..256 bytes: CJK runs, indentation, separators, long words): one warp per
+// piece with the parts held in REGISTERS, part p = slot*32 + lane (8 slots).  One merge per
+// round -- the literal min-rank loop of src/lib.rs:140-196 -- but a round is ~100 instructions
+// and ONE L2 latency: argmin by two hardware warp reductions (redux.sync), neighbours from the
+// alive bitmap (uniform bit scans), the two neighbour probes issued side by side by two lanes.
+// --------------------------------------------------------------------------------------------
+static const int MID_SLOTS = 8;
+static const uint32_t MID_MAX = MID_SLOTS * 32;
+
+struct MidSmem {                       // per-warp merge state: part p = slot*32 + lane -> conflict-free columns
+    uint32_t id[MID_MAX];
+    uint32_t rk[MID_MAX];
+};
+
+// next / previous alive part; `am` is the (warp-uniform) alive bitmap.  The neighbour is almost
+// always in the same 32-part word, so the common case is one select + one bit scan.
+__device__ __forceinline__ uint32_t am_word(const uint32_t (&am)[MID_SLOTS], int w) {
+    uint32_t v = 0;
+#pragma unroll
+    for (int k = 0; k < MID_SLOTS; k++) if (k == w) v = am[k];
+    return v;
+}
+__device__ __forceinline__ int next_alive(const uint32_t (&am)[MID_SLOTS], int p, int n_slots) {
+    const int w0 = p >> 5, b = p & 31;
+    uint32_t m = (b == 31) ? 0u : (am_word(am, w0) & ~((2u << b) - 1u));
+    if (m) return w0 * 32 + __ffs(m) - 1;
+    for (int w = w0 + 1; w < n_slots; w++) { m = am_word(am, w); if (m) return w * 32 + __ffs(m) - 1; }
+    return -1;
+}
+__device__ __forceinline__ int prev_alive(const uint32_t (&am)[MID_SLOTS], int p) {
+    const int w0 = p >> 5, b = p & 31;
+    uint32_t m = am_word(am, w0) & ((1u << b) - 1u);
+    if (m) return w0 * 32 + 31 - __clz((int)m);
+    for (int w = w0 - 1; w >= 0; w--) { m = am_word(am, w); if (m) return w * 32 + 31 - __clz((int)m); }
+    return -1;
+}
+
+__device__ uint32_t mid_piece_warp(const DevTables &T, const uint8_t *__restrict__ piece, uint32_t n, MidSmem &M,
+                                   uint32_t *__restrict__ out, uint32_t *err) {
+    const int lane = threadIdx.x & 31;
+    const uint32_t FULL = 0xFFFFFFFFu;
+    // whole-piece probe (src/lib.rs:367-368); only a token of exactly this length can match
+    if (n <= T.max_token_len && T.n_long_tokens) {
+        uint32_t r = RANK_MAX;
+        if (lane == 0) {
+            uint64_t h = long_hash_init(n);
+            for (uint32_t i = 0; i < n; i += 8) {
+                uint64_t w = 0;
+                for (uint32_t k = 0; k < 8 && i + k < n; k++) w |= (uint64_t)piece[i + k] << (8 * k);
+                h = long_hash_step(h, w);
+            }
+            r = piece_lookup_long(T, h, n, [&](uint32_t i) { return piece[i]; });
+        }
+        r = __shfl_sync(FULL, r, 0);
+        if (r != RANK_MAX) { if (lane == 0) out[0] = r; return 1; }
+    }
+    const int n_slots = (int)((n + 31) >> 5);
+    uint32_t am[MID_SLOTS];
+#pragma unroll
+    for (int s = 0; s < MID_SLOTS; s++) {
+        const uint32_t p = (uint32_t)s * 32u + (uint32_t)lane;
+        uint32_t i0 = 0, r0 = RANK_MAX;
+        if (p < n) {
+            const uint32_t b = piece[p];
+            i0 = __ldg(T.byte_id + b);
+            if (p + 1 < n) r0 = __ldg(T.pair2 + ((b << 8) | piece[p + 1]));
+        }
+        if (s < n_slots) { M.id[p] = i0; M.rk[p] = r0; }
+        am[s] = __ballot_sync(FULL, p < n);
+    }
+    __syncwarp();
+    for (;;) {
+        uint32_t best = RANK_MAX, bp = 0xFFFFu;
+        for (int s = 0; s < n_slots; s++) {
+            const uint32_t r = M.rk[s * 32 + lane];
+            if (r < best) { best = r; bp = (uint32_t)s * 32u + (uint32_t)lane; }
+        }
+        const uint32_t g = __reduce_min_sync(FULL, best);
+        if (g == RANK_MAX) break;
+        const int bj = (int)__reduce_min_sync(FULL, best == g ? bp : 0xFFFFFFFFu);   // leftmost on ties
+        const int j2 = next_alive(am, bj, n_slots);         // right part of the merged pair
+        {
+            const int w2 = j2 >> 5; const uint32_t clr = ~(1u << (j2 & 31));
+#pragma unroll
+            for (int k = 0; k < MID_SLOTS; k++) if (k == w2) am[k] &= clr;
+        }
+        const int j3 = next_alive(am, bj, n_slots);
+        const int jp = prev_alive(am, bj);
+        uint32_t r = RANK_MAX;
+        {   // lane 0 probes (merged, right neighbour), lane 1 (left neighbour, merged): one call site, one latency
+            const int jn = lane == 0 ? j3 : jp;
+            if (lane < 2 && jn >= 0) {
+                const uint32_t o = M.id[jn];
+                r = pair_lookup(T, lane == 0 ? g : o, lane == 0 ? o : g);
+            }
+        }
+        const uint32_t rr = __shfl_sync(FULL, r, 0), rl = __shfl_sync(FULL, r, 1);
+        if (lane == 0) { M.id[bj] = g; M.rk[bj] = (j3 >= 0) ? rr : RANK_MAX; M.rk[j2] = RANK_MAX; if (jp >= 0) M.rk[jp] = rl; }
+        __syncwarp();
+    }
+    uint32_t cnt = 0; bool bad = false;
+#pragma unroll
+    for (int s = 0; s < MID_SLOTS; s++) {
+        const uint32_t m = am[s];
+        if ((m >> lane) & 1u) {
+            const uint32_t x = M.id[s * 32 + lane];
+            out[cnt + __popc(m & ((1u << lane) - 1u))] = x;
+            bad |= x >= PSEUDO_BASE;
+        }
+        cnt += __popc(m);
+    }
+    if (__any_sync(FULL, bad) && lane == 0) atomicOr(err, ERR_NOBYTE);
+    __syncwarp();
+    return cnt;
+}
+
+static const int LONG_WARPS = 8;               // warps per block of long_piece_kernel
 
 __global__ void __launch_bounds__(LONG_WARPS * 32) long_piece_kernel(const uint8_t *__restrict__ text, DevTables T, LongQ q,
                                                                     LongScratch S, uint32_t *ltok, Counters *ctr) {
-    // per-warp merge state for mid-size pieces (CJK runs, indentation, separators): 25 B per byte
-    __shared__ uint32_t s_u32[LONG_WARPS][6][LONG_SMEM_MAX];
-    __shared__ uint8_t s_u8[LONG_WARPS][LONG_SMEM_MAX];
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    __shared__ MidSmem s_mid[LONG_WARPS];
+    const int lane = threadIdx.x & 31;
     const unsigned int n_long = ctr->n_long;
     for (;;) {
         unsigned int i = 0;
@@ -303,16 +420,14 @@ __global__ void __launch_bounds__(LONG_WARPS * 32) long_piece_kernel(const uint8
         if (i >= n_long) break;
         const uint32_t len = q.len[i];
         if (len > GIANT_MIN) continue;                          // handled by giant_piece_kernel (whole block)
-        unsigned long long off = q.off[i];
-        LongScratch P;
-        if (len <= LONG_SMEM_MAX) {
-            P.idA = s_u32[wid][0]; P.rkA = s_u32[wid][1]; P.idB = s_u32[wid][2]; P.rkB = s_u32[wid][3];
-            P.aux1 = s_u32[wid][4]; P.aux2 = s_u32[wid][5]; P.flag = s_u8[wid];
-        } else {
-            P = S;
+        const unsigned long long off = q.off[i];
+        uint32_t nt;
+        if (len <= MID_MAX) nt = mid_piece_warp(T, text + q.start[i], len, s_mid[threadIdx.x >> 5], ltok + off, &ctr->err);
+        else {
+            LongScratch P = S;
             P.idA += off; P.rkA += off; P.idB += off; P.rkB += off; P.aux1 += off; P.aux2 += off; P.flag += off;
+            nt = long_piece_warp(T, text + q.start[i], len, P, ltok + off, &ctr->err);
         }
-        uint32_t nt = long_piece_warp(T, text + q.start[i], len, P, ltok + off, &ctr->err);
         if (lane == 0) q.ntok[i] = nt;
         __syncwarp();
     }
@@ -468,14 +583,13 @@ __device__ uint32_t long_piece_block(const DevTables &T, const uint8_t *__restri
 __global__ void __launch_bounds__(GIANT_THREADS) giant_piece_kernel(const uint8_t *__restrict__ text, DevTables T, LongQ q,
                                                                     LongScratch S, uint32_t *ltok, Counters *ctr) {
     __shared__ unsigned int s_i;
-    const unsigned int n_long = ctr->n_long;
+    const unsigned int n_giant = ctr->n_giant;
     for (;;) {
         __syncthreads();
         if (threadIdx.x == 0) s_i = atomicAdd(&ctr->giant_head, 1u);
         __syncthreads();
-        const unsigned int i = s_i;
-        if (i >= n_long) break;
-        if (q.len[i] <= GIANT_MIN) continue;
+        if (s_i >= n_giant) break;
+        const unsigned int i = q.giant[s_i];
         const unsigned long long off = q.off[i];
         LongScratch P = S;
         P.idA += off; P.rkA += off; P.idB += off; P.rkB += off; P.aux1 += off; P.aux2 += off; P.flag += off;
@@ -859,7 +973,7 @@ struct Slot {
     DevBuf<uint8_t> w_text; DevBuf<unsigned long long> w_docoff, w_tokoff, w_sub_base;
     DevBuf<uint32_t> w_scratch, w_tbits, w_sub_count, w_sub_flags;
     DevBuf<uint32_t> w_dbits, w_pbits, w_sfd, w_lidx, w_out, w_ltok;
-    DevBuf<unsigned long long> w_lq_start, w_lq_off; DevBuf<unsigned int> w_lq_len, w_lq_ntok;
+    DevBuf<unsigned long long> w_lq_start, w_lq_off; DevBuf<unsigned int> w_lq_len, w_lq_ntok, w_lq_giant;
     DevBuf<uint32_t> w_idA, w_rkA, w_idB, w_rkB, w_aux1, w_aux2; DevBuf<uint8_t> w_flag;
     Counters *d_ctr = nullptr; Counters *h_ctr = nullptr;   // h_ctr pinned
     cudaStream_t stream = nullptr;
@@ -880,7 +994,7 @@ struct Slot {
         w_text.release(); w_docoff.release(); w_tokoff.release(); w_sub_base.release();
         w_scratch.release(); w_tbits.release(); w_sub_count.release(); w_sub_flags.release();
         w_dbits.release(); w_pbits.release(); w_sfd.release(); w_lidx.release(); w_out.release(); w_ltok.release();
-        w_lq_start.release(); w_lq_off.release(); w_lq_len.release(); w_lq_ntok.release();
+        w_lq_start.release(); w_lq_off.release(); w_lq_len.release(); w_lq_ntok.release(); w_lq_giant.release();
         w_idA.release(); w_rkA.release(); w_idB.release(); w_rkB.release(); w_aux1.release(); w_aux2.release();
         w_flag.release();
         if (d_ctr) cudaFree(d_ctr);
@@ -1035,7 +1149,8 @@ static int run_pipeline(b200bpe *h, Slot &S, const uint8_t *d_text, uint64_t n_b
     const size_t qcap = (size_t)(n_bytes / (SHORT_MAX + 1)) + 4;
     CUDA_TRY(S.w_lq_start.ensure(qcap)); CUDA_TRY(S.w_lq_off.ensure(qcap));
     CUDA_TRY(S.w_lq_len.ensure(qcap)); CUDA_TRY(S.w_lq_ntok.ensure(qcap));
-    LongQ q{S.w_lq_start.p, S.w_lq_len.p, S.w_lq_off.p, S.w_lq_ntok.p};
+    CUDA_TRY(S.w_lq_giant.ensure((size_t)(n_bytes / (GIANT_MIN + 1)) + 4));
+    LongQ q{S.w_lq_start.p, S.w_lq_len.p, S.w_lq_off.p, S.w_lq_ntok.p, S.w_lq_giant.p};
     uint32_t launches = 0;
 
     CUDA_TRY(cudaEventRecord(S.ev[0], st));
