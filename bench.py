@@ -255,7 +255,7 @@ def main():
 
     # ---- value: device-resident, CUDA events on the launching stream
     for _ in range(args.warmup):
-        step_device()
+        gather_counts(step_device(), n_docs, rank, world, device="cuda")     # also warms the NCCL communicator
     sampler = ClockSampler(local_rank)
     barrier()
     sampler.start()

@@ -302,28 +302,23 @@ static const uint32_t MID_MAX = MID_SLOTS * 32;
 struct MidSmem {                       // per-warp merge state: part p = slot*32 + lane -> conflict-free columns
     uint32_t id[MID_MAX];
     uint32_t rk[MID_MAX];
+    uint32_t am[MID_SLOTS];            // alive bitmap
 };
 
-// next / previous alive part; `am` is the (warp-uniform) alive bitmap.  The neighbour is almost
-// always in the same 32-part word, so the common case is one select + one bit scan.
-__device__ __forceinline__ uint32_t am_word(const uint32_t (&am)[MID_SLOTS], int w) {
-    uint32_t v = 0;
-#pragma unroll
-    for (int k = 0; k < MID_SLOTS; k++) if (k == w) v = am[k];
-    return v;
-}
-__device__ __forceinline__ int next_alive(const uint32_t (&am)[MID_SLOTS], int p, int n_slots) {
+// next / previous alive part.  The neighbour is almost always in the same 32-part word, so the
+// common case is one shared load + one bit scan (all lanes compute the same, uniform, value).
+__device__ __forceinline__ int next_alive(const uint32_t *am, int p, int n_slots) {
     const int w0 = p >> 5, b = p & 31;
-    uint32_t m = (b == 31) ? 0u : (am_word(am, w0) & ~((2u << b) - 1u));
+    uint32_t m = (b == 31) ? 0u : (am[w0] & ~((2u << b) - 1u));
     if (m) return w0 * 32 + __ffs(m) - 1;
-    for (int w = w0 + 1; w < n_slots; w++) { m = am_word(am, w); if (m) return w * 32 + __ffs(m) - 1; }
+    for (int w = w0 + 1; w < n_slots; w++) { m = am[w]; if (m) return w * 32 + __ffs(m) - 1; }
     return -1;
 }
-__device__ __forceinline__ int prev_alive(const uint32_t (&am)[MID_SLOTS], int p) {
+__device__ __forceinline__ int prev_alive(const uint32_t *am, int p) {
     const int w0 = p >> 5, b = p & 31;
-    uint32_t m = am_word(am, w0) & ((1u << b) - 1u);
+    uint32_t m = am[w0] & ((1u << b) - 1u);
     if (m) return w0 * 32 + 31 - __clz((int)m);
-    for (int w = w0 - 1; w >= 0; w--) { m = am_word(am, w); if (m) return w * 32 + 31 - __clz((int)m); }
+    for (int w = w0 - 1; w >= 0; w--) { m = am[w]; if (m) return w * 32 + 31 - __clz((int)m); }
     return -1;
 }
 
@@ -347,9 +342,7 @@ __device__ uint32_t mid_piece_warp(const DevTables &T, const uint8_t *__restrict
         if (r != RANK_MAX) { if (lane == 0) out[0] = r; return 1; }
     }
     const int n_slots = (int)((n + 31) >> 5);
-    uint32_t am[MID_SLOTS];
-#pragma unroll
-    for (int s = 0; s < MID_SLOTS; s++) {
+    for (int s = 0; s < n_slots; s++) {
         const uint32_t p = (uint32_t)s * 32u + (uint32_t)lane;
         uint32_t i0 = 0, r0 = RANK_MAX;
         if (p < n) {
@@ -357,8 +350,9 @@ __device__ uint32_t mid_piece_warp(const DevTables &T, const uint8_t *__restrict
             i0 = __ldg(T.byte_id + b);
             if (p + 1 < n) r0 = __ldg(T.pair2 + ((b << 8) | piece[p + 1]));
         }
-        if (s < n_slots) { M.id[p] = i0; M.rk[p] = r0; }
-        am[s] = __ballot_sync(FULL, p < n);
+        M.id[p] = i0; M.rk[p] = r0;
+        const uint32_t al = __ballot_sync(FULL, p < n);
+        if (lane == 0) M.am[s] = al;
     }
     __syncwarp();
     for (;;) {
@@ -370,14 +364,15 @@ __device__ uint32_t mid_piece_warp(const DevTables &T, const uint8_t *__restrict
         const uint32_t g = __reduce_min_sync(FULL, best);
         if (g == RANK_MAX) break;
         const int bj = (int)__reduce_min_sync(FULL, best == g ? bp : 0xFFFFFFFFu);   // leftmost on ties
-        const int j2 = next_alive(am, bj, n_slots);         // right part of the merged pair
+        const int j2 = next_alive(M.am, bj, n_slots);        // right part of the merged pair
+        int j3 = -1;                                         // part after j2 (the new right neighbour)
         {
-            const int w2 = j2 >> 5; const uint32_t clr = ~(1u << (j2 & 31));
-#pragma unroll
-            for (int k = 0; k < MID_SLOTS; k++) if (k == w2) am[k] &= clr;
+            const int w2 = j2 >> 5, b2 = j2 & 31;
+            uint32_t m = (b2 == 31) ? 0u : (M.am[w2] & ~((2u << b2) - 1u));
+            if (m) j3 = w2 * 32 + __ffs(m) - 1;
+            else for (int w = w2 + 1; w < n_slots; w++) { m = M.am[w]; if (m) { j3 = w * 32 + __ffs(m) - 1; break; } }
         }
-        const int j3 = next_alive(am, bj, n_slots);
-        const int jp = prev_alive(am, bj);
+        const int jp = prev_alive(M.am, bj);
         uint32_t r = RANK_MAX;
         {   // lane 0 probes (merged, right neighbour), lane 1 (left neighbour, merged): one call site, one latency
             const int jn = lane == 0 ? j3 : jp;
@@ -387,13 +382,16 @@ __device__ uint32_t mid_piece_warp(const DevTables &T, const uint8_t *__restrict
             }
         }
         const uint32_t rr = __shfl_sync(FULL, r, 0), rl = __shfl_sync(FULL, r, 1);
-        if (lane == 0) { M.id[bj] = g; M.rk[bj] = (j3 >= 0) ? rr : RANK_MAX; M.rk[j2] = RANK_MAX; if (jp >= 0) M.rk[jp] = rl; }
+        if (lane == 0) {
+            M.id[bj] = g; M.rk[bj] = (j3 >= 0) ? rr : RANK_MAX; M.rk[j2] = RANK_MAX;
+            if (jp >= 0) M.rk[jp] = rl;
+            M.am[j2 >> 5] &= ~(1u << (j2 & 31));
+        }
         __syncwarp();
     }
     uint32_t cnt = 0; bool bad = false;
-#pragma unroll
-    for (int s = 0; s < MID_SLOTS; s++) {
-        const uint32_t m = am[s];
+    for (int s = 0; s < n_slots; s++) {
+        const uint32_t m = M.am[s];
         if ((m >> lane) & 1u) {
             const uint32_t x = M.id[s * 32 + lane];
             out[cnt + __popc(m & ((1u << lane) - 1u))] = x;
