@@ -58,6 +58,7 @@ struct Counters {            // device-resident, zeroed per call
     unsigned int long_head;
     unsigned int giant_head;
     unsigned int n_giant;
+    unsigned int n_big;
     unsigned int ticket;
     unsigned int err;
     unsigned long long total_tokens;
@@ -95,47 +96,74 @@ __global__ void mark_docs_kernel(const unsigned long long *__restrict__ doc_off,
 template <int PAT>
 __global__ void __launch_bounds__(256) pretok_kernel(const uint8_t *__restrict__ text, long long n_bytes,
                                                      const uint32_t *__restrict__ dbits, UcTables uc,
-                                                     uint32_t *__restrict__ pbits, long long n_words) {
+                                                     uint32_t *__restrict__ pbits, uint32_t *__restrict__ psum,
+                                                     long long n_words) {
     long long w = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    if (w >= n_words) return;
-    TextAccess t{text, n_bytes, dbits, uc.stage1, uc.stage2, uc.ascii};
-    pbits[w] = span_boundaries<PAT>(t, w);            // pretok_fast.cuh (+ pretok_rules.cuh for the rare cases)
+    uint32_t word = 0;
+    if (w < n_words) {
+        TextAccess t{text, n_bytes, dbits, uc.stage1, uc.stage2, uc.ascii};
+        word = span_boundaries<PAT>(t, w);            // pretok_fast.cuh (+ pretok_rules.cuh for the rare cases)
+        pbits[w] = word;
+    }
+    // summary bitmap: bit = "this word of pbits has a piece start" (lets find_long skip long runs 32x faster)
+    const uint32_t nz = __ballot_sync(0xFFFFFFFFu, word != 0);
+    if ((threadIdx.x & 31) == 0 && (w >> 5) <= ((n_words - 1) >> 5)) psum[w >> 5] = nz;
 }
 
 // single-piece mode (encode_single_piece): P = {0, n_bytes}
-__global__ void single_piece_bits_kernel(uint32_t *pbits, long long n_bytes, long long n_words) {
+__global__ void single_piece_bits_kernel(uint32_t *pbits, uint32_t *psum, long long n_bytes, long long n_words) {
     long long w = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    if (w >= n_words) return;
     uint32_t word = 0;
-    if (w == 0) word |= 1u;
-    if ((n_bytes >> 5) == w) word |= 1u << (n_bytes & 31);
-    pbits[w] = word;
+    if (w < n_words) {
+        if (w == 0) word |= 1u;
+        if ((n_bytes >> 5) == w) word |= 1u << (n_bytes & 31);
+        pbits[w] = word;
+    }
+    const uint32_t nz = __ballot_sync(0xFFFFFFFFu, word != 0);
+    if ((threadIdx.x & 31) == 0 && (w >> 5) <= ((n_words - 1) >> 5)) psum[w >> 5] = nz;
 }
 
 // --------------------------------------------------------------------------------------------
 // kernel 2: find pieces longer than SHORT_MAX bytes
 // --------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) find_long_kernel(const uint32_t *__restrict__ pbits, long long n_bytes,
+__global__ void __launch_bounds__(256) find_long_kernel(const uint32_t *__restrict__ pbits,
+                                                        const uint32_t *__restrict__ psum, long long n_bytes,
                                                         long long n_words, LongQ q, uint32_t *lidx,
                                                         Counters *ctr) {
     long long w = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (w >= n_words) return;
-    uint32_t m = pbits[w];
-    while (m) {
-        int j = __ffs(m) - 1; m &= m - 1;
-        long long s = w * 32 + j;
+    const uint32_t pw = pbits[w];
+    if (pw == 0) return;
+    // bit-parallel filter: a start at bit j is "long" iff the 16 bits after it are all zero
+    uint32_t cand;
+    {
+        const uint64_t x = ((uint64_t)pbits[w + 1] << 32) | pw;      // pbits has zeroed tail words
+        uint64_t z = ~x;
+        z &= z >> 1; z &= z >> 2; z &= z >> 4; z &= z >> 8;           // bit i: x[i .. i+15] are all zero
+        cand = pw & (uint32_t)(z >> 1);
+    }
+    for (uint32_t mm = cand; mm;) {
+        const int j = __ffs(mm) - 1; mm &= mm - 1;
+        const long long s = w * 32 + j;
         if (s >= n_bytes) break;
+        const uint32_t m = (j == 31) ? 0u : (pw & ~((2u << j) - 1u));     // piece starts after j in this word
         long long nxt;
         if (m) nxt = w * 32 + (__ffs(m) - 1);
         else {
             long long w2 = w + 1;
             uint32_t x = pbits[w2];
-            if (x == 0) {                                       // definitely long: find the end
-                do { w2++; x = pbits[w2]; } while (x == 0);     // the sentinel bit at n_bytes stops this
+            if (x == 0) {
+                // finish the current group of 32 words, then hop over whole groups via the summary bitmap
+                // (the sentinel bit at n_bytes guarantees termination)
+                uint32_t sm = ((w2 & 31) == 31) ? 0u : (psum[w2 >> 5] & ~((2u << (w2 & 31)) - 1u));
+                long long grp = w2 >> 5;
+                while (sm == 0) { grp++; sm = psum[grp]; }
+                w2 = grp * 32 + (__ffs(sm) - 1);
+                x = pbits[w2];
             }
             nxt = w2 * 32 + (__ffs(x) - 1);
         }
-        long long len = nxt - s;
+        const long long len = nxt - s;
         if (len > SHORT_MAX) {
             unsigned int i = atomicAdd(&ctr->n_long, 1u);
             unsigned long long off = atomicAdd(&ctr->long_bytes, (unsigned long long)len);
@@ -614,6 +642,7 @@ struct TileParams {
     uint32_t *sub_flags;          // [n_sub] bit0: has long piece, bit1: has document start, bits 8..: straddling tokens
     unsigned long long *sub_base; // [n_sub+1] exclusive prefix of sub_count (kernel 5)
     uint32_t *out; unsigned long long *tok_off;
+    unsigned long long *big_dst, *big_src; uint32_t *big_n;   // token copies too large for one warp (kernel 7)
     Counters *ctr;
 };
 
@@ -828,14 +857,29 @@ __global__ void __launch_bounds__(ENC_WARPS * 32) encode_tiles_kernel(TileParams
 // --------------------------------------------------------------------------------------------
 // kernel 5: exclusive scan of the per-sub-tile token counts (single block; n_sub ~ N / 1024)
 // --------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(1024) scan_counts_kernel(const uint32_t *__restrict__ cnt, long long n,
-                                                           unsigned long long *__restrict__ base, Counters *ctr) {
+static const int SCAN_ITEMS = 4096;                 // counts per block of the two-level scan
+
+__global__ void __launch_bounds__(256) scan_partial_kernel(const uint32_t *__restrict__ cnt, long long n,
+                                                          unsigned long long *__restrict__ part) {
+    __shared__ unsigned long long s_w[8];
+    const long long lo = (long long)blockIdx.x * SCAN_ITEMS;
+    unsigned long long sum = 0;
+    for (int k = threadIdx.x; k < SCAN_ITEMS; k += 256) { long long i = lo + k; if (i < n) sum += cnt[i]; }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(0xFFFFFFFFu, sum, o);
+    if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = sum;
+    __syncthreads();
+    if (threadIdx.x == 0) { unsigned long long t = 0; for (int i = 0; i < 8; i++) t += s_w[i]; part[blockIdx.x] = t; }
+}
+
+// single block: exclusive scan of the per-block partial sums (n_blocks <= a few thousand)
+__global__ void __launch_bounds__(1024) scan_top_kernel(unsigned long long *part, long long n_blocks, Counters *ctr) {
     __shared__ unsigned long long s_part[1024];
     const int tid = threadIdx.x;
-    const long long per = (n + 1023) / 1024;
-    const long long lo = tid * per, hi = (lo + per < n) ? lo + per : n;
+    const long long per = (n_blocks + 1023) / 1024;
+    const long long lo = tid * per, hi = (lo + per < n_blocks) ? lo + per : n_blocks;
     unsigned long long sum = 0;
-    for (long long i = lo; i < hi; i++) sum += cnt[i];
+    for (long long i = lo; i < hi; i++) sum += part[i];
     s_part[tid] = sum;
     __syncthreads();
     for (int o = 1; o < 1024; o <<= 1) {
@@ -845,8 +889,29 @@ __global__ void __launch_bounds__(1024) scan_counts_kernel(const uint32_t *__res
         __syncthreads();
     }
     unsigned long long run = s_part[tid] - sum;
-    for (long long i = lo; i < hi; i++) { base[i] = run; run += cnt[i]; }
-    if (tid == 1023) { base[n] = s_part[1023]; ctr->total_tokens = s_part[1023]; }
+    for (long long i = lo; i < hi; i++) { unsigned long long c = part[i]; part[i] = run; run += c; }
+    if (tid == 1023) ctr->total_tokens = s_part[1023];
+}
+
+__global__ void __launch_bounds__(256) scan_final_kernel(const uint32_t *__restrict__ cnt, long long n,
+                                                        const unsigned long long *__restrict__ part,
+                                                        unsigned long long *__restrict__ base, const Counters *ctr) {
+    __shared__ unsigned long long s_w[8];
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const long long lo = (long long)blockIdx.x * SCAN_ITEMS + (long long)tid * 16;   // 16 consecutive counts per thread
+    uint32_t c[16]; unsigned long long sum = 0;
+#pragma unroll
+    for (int k = 0; k < 16; k++) { long long i = lo + k; c[k] = (i < n) ? cnt[i] : 0u; sum += c[k]; }
+    unsigned long long inc = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { unsigned long long y = __shfl_up_sync(0xFFFFFFFFu, inc, o); if (lane >= o) inc += y; }
+    if (lane == 31) s_w[wid] = inc;
+    __syncthreads();
+    unsigned long long run = part[blockIdx.x] + inc - sum;
+    for (int i = 0; i < wid; i++) run += s_w[i];
+#pragma unroll
+    for (int k = 0; k < 16; k++) { long long i = lo + k; if (i < n) base[i] = run; run += c[k]; }
+    if (blockIdx.x == 0 && tid == 0) base[n] = ctr->total_tokens;
 }
 
 // chunked host path: rebase a slice of the caller's document offsets / globalise token offsets
@@ -926,7 +991,22 @@ __global__ void __launch_bounds__(256) gather_kernel(TileParams p) {
         const unsigned long long dst = __shfl_sync(0xFFFFFFFFu, big_dst, src_lane);
         const unsigned long long bs = __shfl_sync(0xFFFFFFFFu, big_src, src_lane);
         const uint32_t nt = __shfl_sync(0xFFFFFFFFu, big_n, src_lane);
+        if (nt > 4096) {                                   // giant piece: leave it to the whole grid (kernel 7)
+            if (lane == 0) { const uint32_t e = atomicAdd(&p.ctr->n_big, 1u); p.big_dst[e] = dst; p.big_src[e] = bs; p.big_n[e] = nt; }
+            continue;
+        }
         for (uint32_t x = lane; x < nt; x += 32) p.out[dst + x] = p.ltok[bs + x];
+    }
+}
+
+// kernel 7: token copies of giant pieces, spread over the whole grid
+__global__ void __launch_bounds__(256) big_copy_kernel(TileParams p) {
+    const unsigned int nb = p.ctr->n_big;
+    for (unsigned int e = 0; e < nb; e++) {
+        const unsigned long long dst = p.big_dst[e], src = p.big_src[e];
+        const uint32_t n = p.big_n[e];
+        for (unsigned long long x = blockIdx.x * 256ull + threadIdx.x; x < n; x += (unsigned long long)gridDim.x * 256ull)
+            p.out[dst + x] = p.ltok[src + x];
     }
 }
 
@@ -970,8 +1050,8 @@ struct PinnedBuf {
 struct Slot {
     DevBuf<uint8_t> w_text; DevBuf<unsigned long long> w_docoff, w_tokoff, w_sub_base;
     DevBuf<uint32_t> w_scratch, w_tbits, w_sub_count, w_sub_flags;
-    DevBuf<uint32_t> w_dbits, w_pbits, w_sfd, w_lidx, w_out, w_ltok;
-    DevBuf<unsigned long long> w_lq_start, w_lq_off; DevBuf<unsigned int> w_lq_len, w_lq_ntok, w_lq_giant;
+    DevBuf<uint32_t> w_dbits, w_pbits, w_psum, w_sfd, w_lidx, w_out, w_ltok;
+    DevBuf<unsigned long long> w_lq_start, w_lq_off; DevBuf<unsigned int> w_lq_len, w_lq_ntok, w_lq_giant, w_big_n; DevBuf<unsigned long long> w_big_dst, w_big_src, w_scan_part;
     DevBuf<uint32_t> w_idA, w_rkA, w_idB, w_rkB, w_aux1, w_aux2; DevBuf<uint8_t> w_flag;
     Counters *d_ctr = nullptr; Counters *h_ctr = nullptr;   // h_ctr pinned
     cudaStream_t stream = nullptr;
@@ -991,8 +1071,8 @@ struct Slot {
     void destroy() {
         w_text.release(); w_docoff.release(); w_tokoff.release(); w_sub_base.release();
         w_scratch.release(); w_tbits.release(); w_sub_count.release(); w_sub_flags.release();
-        w_dbits.release(); w_pbits.release(); w_sfd.release(); w_lidx.release(); w_out.release(); w_ltok.release();
-        w_lq_start.release(); w_lq_off.release(); w_lq_len.release(); w_lq_ntok.release(); w_lq_giant.release();
+        w_dbits.release(); w_pbits.release(); w_psum.release(); w_sfd.release(); w_lidx.release(); w_out.release(); w_ltok.release();
+        w_lq_start.release(); w_lq_off.release(); w_lq_len.release(); w_lq_ntok.release(); w_lq_giant.release(); w_big_n.release(); w_big_dst.release(); w_big_src.release(); w_scan_part.release();
         w_idA.release(); w_rkA.release(); w_idB.release(); w_rkB.release(); w_aux1.release(); w_aux2.release();
         w_flag.release();
         if (d_ctr) cudaFree(d_ctr);
@@ -1138,8 +1218,10 @@ static int run_pipeline(b200bpe *h, Slot &S, const uint8_t *d_text, uint64_t n_b
     const long long n_tiles = (n_words + 31) / 32;                  // 1 KiB sub-tiles, one warp each
     CUDA_TRY(S.w_dbits.ensure((size_t)n_words + 4));
     CUDA_TRY(S.w_pbits.ensure((size_t)n_words + 4));
+    CUDA_TRY(S.w_psum.ensure((size_t)(n_words >> 5) + 4));
     CUDA_TRY(S.w_sfd.ensure((size_t)n_words + 4));
     CUDA_TRY(S.w_sub_base.ensure((size_t)n_tiles + 2));
+    CUDA_TRY(S.w_scan_part.ensure((size_t)(n_tiles / SCAN_ITEMS) + 4));
     CUDA_TRY(S.w_sub_count.ensure((size_t)n_tiles + 2)); CUDA_TRY(S.w_sub_flags.ensure((size_t)n_tiles + 2));
     CUDA_TRY(S.w_tbits.ensure((size_t)n_words + 4));
     CUDA_TRY(S.w_scratch.ensure((size_t)n_tiles * SUB_CAP + 64));
@@ -1148,6 +1230,8 @@ static int run_pipeline(b200bpe *h, Slot &S, const uint8_t *d_text, uint64_t n_b
     CUDA_TRY(S.w_lq_start.ensure(qcap)); CUDA_TRY(S.w_lq_off.ensure(qcap));
     CUDA_TRY(S.w_lq_len.ensure(qcap)); CUDA_TRY(S.w_lq_ntok.ensure(qcap));
     CUDA_TRY(S.w_lq_giant.ensure((size_t)(n_bytes / (GIANT_MIN + 1)) + 4));
+    CUDA_TRY(S.w_big_n.ensure((size_t)(n_bytes / (GIANT_MIN + 1)) + 4));
+    CUDA_TRY(S.w_big_dst.ensure((size_t)(n_bytes / (GIANT_MIN + 1)) + 4)); CUDA_TRY(S.w_big_src.ensure((size_t)(n_bytes / (GIANT_MIN + 1)) + 4));
     LongQ q{S.w_lq_start.p, S.w_lq_len.p, S.w_lq_off.p, S.w_lq_ntok.p, S.w_lq_giant.p};
     uint32_t launches = 0;
 
@@ -1165,19 +1249,19 @@ static int run_pipeline(b200bpe *h, Slot &S, const uint8_t *d_text, uint64_t n_b
     CUDA_TRY(cudaEventRecord(S.ev[1], st));
     {
         unsigned grid = (unsigned)((n_words + 255) / 256);
-        if (single_piece) single_piece_bits_kernel<<<grid, 256, 0, st>>>(S.w_pbits.p, (long long)n_bytes, n_words);
+        if (single_piece) single_piece_bits_kernel<<<grid, 256, 0, st>>>(S.w_pbits.p, S.w_psum.p, (long long)n_bytes, n_words);
         else if (h->pattern == PAT_R50K)
-            pretok_kernel<PAT_R50K><<<grid, 256, 0, st>>>(d_text, (long long)n_bytes, S.w_dbits.p, h->uc, S.w_pbits.p, n_words);
+            pretok_kernel<PAT_R50K><<<grid, 256, 0, st>>>(d_text, (long long)n_bytes, S.w_dbits.p, h->uc, S.w_pbits.p, S.w_psum.p, n_words);
         else if (h->pattern == PAT_CL100K)
-            pretok_kernel<PAT_CL100K><<<grid, 256, 0, st>>>(d_text, (long long)n_bytes, S.w_dbits.p, h->uc, S.w_pbits.p, n_words);
+            pretok_kernel<PAT_CL100K><<<grid, 256, 0, st>>>(d_text, (long long)n_bytes, S.w_dbits.p, h->uc, S.w_pbits.p, S.w_psum.p, n_words);
         else
-            pretok_kernel<PAT_O200K><<<grid, 256, 0, st>>>(d_text, (long long)n_bytes, S.w_dbits.p, h->uc, S.w_pbits.p, n_words);
+            pretok_kernel<PAT_O200K><<<grid, 256, 0, st>>>(d_text, (long long)n_bytes, S.w_dbits.p, h->uc, S.w_pbits.p, S.w_psum.p, n_words);
         launches++;
     }
     CUDA_TRY(cudaEventRecord(S.ev[2], st));
     {
         unsigned grid = (unsigned)((n_words + 255) / 256);
-        find_long_kernel<<<grid, 256, 0, st>>>(S.w_pbits.p, (long long)n_bytes, n_words, q, S.w_lidx.p, S.d_ctr);
+        find_long_kernel<<<grid, 256, 0, st>>>(S.w_pbits.p, S.w_psum.p, (long long)n_bytes, n_words, q, S.w_lidx.p, S.d_ctr);
         launches++;
     }
     const bool presized = n_bytes <= PRESIZE_LIMIT;
@@ -1211,11 +1295,18 @@ static int run_pipeline(b200bpe *h, Slot &S, const uint8_t *d_text, uint64_t n_b
         p.scratch = S.w_scratch.p; p.tbits = S.w_tbits.p; p.sub_count = S.w_sub_count.p;
         p.sub_flags = S.w_sub_flags.p; p.sub_base = S.w_sub_base.p;
         p.out = d_out; p.tok_off = d_tok_off; p.ctr = S.d_ctr;
+        p.big_dst = S.w_big_dst.p; p.big_src = S.w_big_src.p; p.big_n = S.w_big_n.p;
         encode_tiles_kernel<<<(unsigned)((n_tiles + ENC_WARPS - 1) / ENC_WARPS), ENC_WARPS * 32, 0, st>>>(p, h->T);
         CUDA_TRY(cudaEventRecord(S.ev[7], st));
-        scan_counts_kernel<<<1, 1024, 0, st>>>(S.w_sub_count.p, n_tiles, S.w_sub_base.p, S.d_ctr);
+        {
+            const long long nb = (n_tiles + SCAN_ITEMS - 1) / SCAN_ITEMS;
+            scan_partial_kernel<<<(unsigned)nb, 256, 0, st>>>(S.w_sub_count.p, n_tiles, S.w_scan_part.p);
+            scan_top_kernel<<<1, 1024, 0, st>>>(S.w_scan_part.p, nb, S.d_ctr);
+            scan_final_kernel<<<(unsigned)nb, 256, 0, st>>>(S.w_sub_count.p, n_tiles, S.w_scan_part.p, S.w_sub_base.p, S.d_ctr);
+        }
         gather_kernel<<<(unsigned)((n_tiles + 7) / 8), 256, 0, st>>>(p);
-        launches += 3;
+        big_copy_kernel<<<148 * 2, 256, 0, st>>>(p);
+        launches += 6;
     }
     CUDA_TRY(cudaEventRecord(S.ev[4], st));
     CUDA_TRY(cudaMemcpyAsync(S.h_ctr, S.d_ctr, sizeof(Counters), cudaMemcpyDeviceToHost, st));
