@@ -163,6 +163,7 @@ def main():
     ap.add_argument("--bytes", type=int, default=0, help="override the per-rank corpus size (development)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--decode", action="store_true", help="also time the device decode of the produced tokens (next row)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
@@ -344,6 +345,19 @@ def main():
                 "h2d_ms": e2e_tm["h2d_ms"], "d2h_ms": e2e_tm["d2h_ms"], "device_ms": e2e_tm["device_total_ms"]},
         "clocks": clocks,
     }
+    if args.decode and world == 1:
+        buf = enc.encode_ordinary_packed(h_text_np, h_off_np)
+        dtoks, doffs = np.array(buf.tokens()), np.array(buf.offsets())
+        buf.close()
+        enc.decode_packed(dtoks, doffs)
+        dt = []
+        for _ in range(3):
+            t0 = time.perf_counter()
+            data, boff = enc.decode_packed(dtoks, doffs)
+            dt.append(time.perf_counter() - t0)
+        assert len(data) == N
+        line["decode"] = {"value": N / float(np.mean(dt)) / 1e9, "unit": "GB/s of decoded bytes (host tokens -> host bytes)",
+                          "device_ms": core.last_timings()["device_total_ms"], "ms_per_step": float(np.mean(dt)) * 1e3}
     if not args.no_cpu_baseline and world == 1:
         gbs, mts, desc = cpu_reference_run(pat, ranks, special, text, off, args.cpu_seconds, cores)
         line["cpu_baseline"] = {"value": gbs, "unit": "GB/s", "mtokens_per_s": mts, **desc}

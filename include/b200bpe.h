@@ -87,6 +87,14 @@ void b200bpe_result_free(b200bpe_result_t *r);
 int b200bpe_decode_bytes(b200bpe_t *h, const uint32_t *tokens, uint64_t n_tokens, uint8_t *out,
                          uint64_t out_cap, uint64_t *out_len, uint32_t *bad_token);
 
+/* Batched decode on the device ("next" row): CoreBPE::decode_bytes (src/lib.rs:345-358) as fanned out
+ * by Encoding.decode_bytes_batch (tiktoken/core.py:345-350).  HOST buffers: tokens of all documents
+ * concatenated, tok_off[n_docs+1].  The result reuses b200bpe_result: b200bpe_result_tokens() points
+ * at the BYTES (b200bpe_result_n_tokens() = byte count), b200bpe_result_offsets() at the per-document
+ * byte offsets.  Unknown id -> B200BPE_EKEY with *bad_token set (KeyError, py.rs:160). */
+int b200bpe_decode_batch(b200bpe_t *h, const uint32_t *tokens, const uint64_t *tok_off, uint64_t n_docs,
+                         b200bpe_result_t **out, uint32_t *bad_token);
+
 /* Per-stage device timings (ms, CUDA events on the engine stream) of the most recent encode
  * call on this handle: [0] mark documents, [1] pre-tokenise, [2] long-piece scan + merge,
  * [3] encode kernel, [4] total device time, [5] H2D, [6] D2H, [7] count scan + gather.

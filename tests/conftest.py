@@ -29,6 +29,7 @@ def hostcheck():
     import ctypes as C
     H = C.CDLL(_build_hostcheck())
     H.hc_piece_starts.argtypes = [C.c_int, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p]
+    H.hc_piece_starts_fast.argtypes = [C.c_int, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
     H.hc_tables_new.restype = C.c_void_p
     H.hc_tables_new.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]
     H.hc_tables_free.argtypes = [C.c_void_p]

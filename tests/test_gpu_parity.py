@@ -176,3 +176,20 @@ def test_device_resident_entry_point():
     assert n == len(exp_t)
     assert np.array_equal(d_tok[:n].cpu().numpy().view(np.uint32), exp_t)
     assert np.array_equal(d_toff.cpu().numpy().astype(np.uint64), exp_o)
+
+
+def test_device_decode_batch_roundtrip_and_errors():
+    """"next" row: CoreBPE::decode_bytes (src/lib.rs:345-358) as one device gather per batch."""
+    e, o, special = get("o200k_base")
+    text, off = corpus.config3(nbytes=6 << 20, seed=5)
+    buf = e.encode_ordinary_packed(text, off)
+    toks, toff = np.array(buf.tokens()), np.array(buf.offsets()); buf.close()
+    data, boff = e.decode_packed(toks, toff)
+    assert np.array_equal(data, text) and np.array_equal(boff, off)           # decode(encode(x)) == x, per document
+    docs = ["hello world", "", "x" * 5000, "日本語 <|endoftext|>", "\n\n  a"]
+    enc = e.encode_batch(docs, allowed_special="all")
+    assert e.decode_batch(enc) == docs
+    assert e.decode_bytes_batch(enc) == [e.decode_bytes(t) for t in enc]    # same as the per-call table read
+    assert e.decode_bytes_batch([]) == [] and e.decode_bytes_batch([[], []]) == [b"", b""]
+    with pytest.raises(KeyError):
+        e.decode_bytes_batch([[1, 2, 10 ** 7]])

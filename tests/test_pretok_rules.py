@@ -28,6 +28,20 @@ def rule_starts(H, pid, docs):
     return out[:n], off
 
 
+def fast_starts(H, pid, docs):
+    """The bit-parallel span evaluator the kernel runs (pretok_fast.cuh); also returns slow-path stats."""
+    blob = b"".join(docs)
+    n = len(blob)
+    off = np.zeros(len(docs) + 1, np.uint64)
+    off[1:] = np.cumsum([len(d) for d in docs])
+    a = np.frombuffer(blob, np.uint8) if n else np.zeros(1, np.uint8)
+    out = np.zeros(n + 2, np.uint8)
+    st = np.zeros(2, np.uint64)
+    assert H.hc_piece_starts_fast(pid, a.ctypes.data, n, off.ctypes.data, len(docs), out.ctypes.data, st.ctypes.data) == 0
+    assert out[n] == 1                          # end sentinel
+    return out[:n], off, st
+
+
 def expected_starts(o, doc):
     exp = np.zeros(len(doc), np.uint8)
     p = 0
@@ -93,4 +107,52 @@ def test_documents_are_separate_haystacks(hostcheck):
     got, _ = rule_starts(hostcheck, 1, [b"a  b"])
     assert got.tolist() == [1, 1, 1, 0]
     got, _ = rule_starts(hostcheck, 1, [b"", b"", b"x", b""])
+    assert got.tolist() == [1]
+
+
+@pytest.mark.parametrize("name", ["r50k", "cl100k", "o200k"])
+def test_fast_path_exhaustive(hostcheck, name):
+    """pretok_fast.cuh (SWAR masks + slow-path fallback) == literal matcher, every string up to L-1."""
+    pid, pat = PATS[name]
+    spec = json.load(open(os.path.join(G, "splits_exhaustive.json")))[name]
+    o = Oracle(BYTES, {}, pat)
+    for l in range(1, spec["max_len"]):
+        docs = ["".join(t).encode() for t in itertools.product(spec["alphabet"], repeat=l)]
+        got, off, _ = fast_starts(hostcheck, pid, docs)
+        for i, d in enumerate(docs):
+            assert np.array_equal(got[int(off[i]):int(off[i + 1])], expected_starts(o, d)), (name, d)
+
+
+@pytest.mark.parametrize("name", ["r50k", "cl100k", "o200k"])
+def test_fast_path_on_reference_unicode_cases_and_corpus(hostcheck, name):
+    pid, pat = PATS[name]
+    cases = json.load(open(os.path.join(G, "splits_random.json")))[name]
+    docs = [bytes.fromhex(t) for t, _ in cases]
+    got, off, _ = fast_starts(hostcheck, pid, docs)
+    for i, (t, pieces) in enumerate(cases):
+        exp = np.zeros(len(docs[i]), np.uint8)
+        p = 0
+        for ph in pieces:
+            exp[p] = 1
+            p += len(ph) // 2
+        assert np.array_equal(got[int(off[i]):int(off[i + 1])], exp), docs[i]
+    # seeded corpus of the matching kind, cut into documents at arbitrary scalar boundaries
+    from tools import corpus
+    kind = {"r50k": corpus.CODE, "cl100k": corpus.ENGLISH, "o200k": corpus.MIXED}[name]
+    text = corpus.generate(kind, 321, 1 << 20)
+    _, doff = corpus.docs_fixed(text, 40000, at_space=False)
+    cdocs = [text[int(doff[i]):int(doff[i + 1])].tobytes() for i in range(len(doff) - 1)]
+    o = Oracle(BYTES, {}, pat)
+    got, off, st = fast_starts(hostcheck, pid, cdocs)
+    for i, d in enumerate(cdocs):
+        assert np.array_equal(got[int(off[i]):int(off[i + 1])], expected_starts(o, d))
+    assert st[1] < 0.1 * st[0]                  # the slow path stays the exception
+
+
+def test_fast_path_documents_are_separate_haystacks(hostcheck):
+    got, _, _ = fast_starts(hostcheck, 1, [b"a  ", b"b"])
+    assert got.tolist() == [1, 1, 0, 1]
+    got, _, _ = fast_starts(hostcheck, 1, [b"a  b"])
+    assert got.tolist() == [1, 1, 1, 0]
+    got, _, _ = fast_starts(hostcheck, 2, [b"", b"", b"x", b""])
     assert got.tolist() == [1]

@@ -74,6 +74,8 @@ def lib() -> C.CDLL:
     L.b200bpe_result_free.argtypes = [vp]
     L.b200bpe_decode_bytes.restype = i32
     L.b200bpe_decode_bytes.argtypes = [vp, vp, u64, vp, u64, C.POINTER(u64), C.POINTER(u32)]
+    L.b200bpe_decode_batch.restype = i32
+    L.b200bpe_decode_batch.argtypes = [vp, vp, vp, u64, C.POINTER(vp), C.POINTER(u32)]
     L.b200bpe_last_timings.restype = i32
     L.b200bpe_last_timings.argtypes = [vp, vp, C.POINTER(u32)]
     L.b200bpe_table_bytes.restype = i32
@@ -88,7 +90,7 @@ EXPORTS = [
     "b200bpe_create", "b200bpe_destroy", "b200bpe_encode_ordinary_batch", "b200bpe_encode_batch",
     "b200bpe_encode_device", "b200bpe_encode_single_piece", "b200bpe_result_tokens",
     "b200bpe_result_offsets", "b200bpe_result_n_tokens", "b200bpe_result_n_docs", "b200bpe_result_free",
-    "b200bpe_decode_bytes", "b200bpe_last_timings", "b200bpe_table_bytes", "b200bpe_last_error",
+    "b200bpe_decode_bytes", "b200bpe_decode_batch", "b200bpe_last_timings", "b200bpe_table_bytes", "b200bpe_last_error",
     "b200bpe_version",
 ]
 

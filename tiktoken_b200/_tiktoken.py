@@ -201,6 +201,38 @@ class CoreBPE:
                 return out[:out_len.value].tobytes()
             cap = int(out_len.value)
 
+    def decode_batch_buffer(self, tokens: np.ndarray, tok_off: np.ndarray):
+        """Device gather ("next" row): tokens uint32[T] + tok_off uint64[n_docs+1] -> (bytes uint8[B], byte_off
+        uint64[n_docs+1]).  KeyError on an unknown id, like decode_bytes."""
+        tokens = np.ascontiguousarray(tokens, np.uint32)
+        tok_off = np.ascontiguousarray(tok_off, np.uint64)
+        res = C.c_void_p()
+        bad = C.c_uint32(0)
+        rc = self._L.b200bpe_decode_batch(self._h, _ptr(tokens if len(tokens) else np.zeros(1, np.uint32)), _ptr(tok_off),
+                                          len(tok_off) - 1, C.byref(res), C.byref(bad))
+        if rc == _lib.EKEY:
+            raise KeyError(f"Invalid token for decoding: {bad.value}")
+        _lib.check(rc)
+        n_bytes = int(self._L.b200bpe_result_n_tokens(res))
+        n_docs = int(self._L.b200bpe_result_n_docs(res))
+        data = np.ctypeslib.as_array(C.cast(self._L.b200bpe_result_tokens(res), C.POINTER(C.c_uint8)),
+                                     shape=(max(n_bytes, 1),))[:n_bytes].copy()
+        off = np.ctypeslib.as_array(C.cast(self._L.b200bpe_result_offsets(res), C.POINTER(C.c_uint64)),
+                                    shape=(n_docs + 1,)).copy()
+        self._L.b200bpe_result_free(res)
+        return data, off
+
+    def decode_bytes_batch(self, batch) -> list[bytes]:
+        lens = np.fromiter((len(t) for t in batch), dtype=np.uint64, count=len(batch))
+        off = np.zeros(len(batch) + 1, np.uint64)
+        np.cumsum(lens, out=off[1:])
+        toks = np.zeros(int(off[-1]), np.uint32)
+        for i, t in enumerate(batch):
+            toks[int(off[i]):int(off[i + 1])] = np.asarray(t, dtype=np.uint32)
+        data, boff = self.decode_batch_buffer(toks, off)
+        raw = data.tobytes()
+        return [raw[int(boff[i]):int(boff[i + 1])] for i in range(len(batch))]
+
     def decode_single_token_bytes(self, token: int) -> bytes:                # py.rs:164-172
         if self._decoder is None:
             self._decoder = {v: k for k, v in self._encoder.items()}

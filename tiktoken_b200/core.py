@@ -169,10 +169,15 @@ class Encoding:
         return b"".join(pieces).decode("utf-8", errors="strict"), offsets
 
     def decode_batch(self, batch: Sequence[Sequence[int]], *, errors: str = "replace", num_threads: int = 8) -> list[str]:
-        return [self.decode(t, errors=errors) for t in batch]
+        """One native call: device gather of the token byte strings (reference: thread pool, core.py:337-343)."""
+        return [b.decode("utf-8", errors=errors) for b in self._core_bpe.decode_bytes_batch(batch)]
 
     def decode_bytes_batch(self, batch: Sequence[Sequence[int]], *, num_threads: int = 8) -> list[bytes]:
-        return [self.decode_bytes(t) for t in batch]
+        return self._core_bpe.decode_bytes_batch(batch)
+
+    def decode_packed(self, tokens: np.ndarray, tok_off: np.ndarray):
+        """Array form: tokens uint32[T] + offsets uint64[n_docs+1] -> (bytes uint8[B], byte offsets uint64[n_docs+1])."""
+        return self._core_bpe.decode_batch_buffer(tokens, tok_off)
 
     # ---------------------------------------------------------------- misc
     def token_byte_values(self) -> list[bytes]:

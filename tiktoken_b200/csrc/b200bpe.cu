@@ -1011,6 +1011,46 @@ __global__ void __launch_bounds__(256) big_copy_kernel(TileParams p) {
 }
 
 // --------------------------------------------------------------------------------------------
+// decode ("next" row): CoreBPE::decode_bytes (src/lib.rs:345-358) for a whole batch -- token id ->
+// byte string gather.  Length look-up, two-level scan (the same scan kernels), copy.
+// --------------------------------------------------------------------------------------------
+static const uint32_t ERR_BADTOKEN = 4u;
+
+__global__ void __launch_bounds__(256) decode_len_kernel(const uint32_t *__restrict__ tokens, unsigned long long n,
+                                                        const uint32_t *__restrict__ tok_boff, uint32_t n_ids,
+                                                        uint32_t *__restrict__ len, Counters *ctr) {
+    unsigned long long i = blockIdx.x * 256ull + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t t = tokens[i];
+    uint32_t l = 0;
+    if (t < n_ids) l = __ldg(tok_boff + t + 1) - __ldg(tok_boff + t);
+    if (l == 0) {                                           // unknown id (every real token has >= 1 byte)
+        if (atomicOr(&ctr->err, ERR_BADTOKEN) == 0 || true) atomicMin(&ctr->ticket, (unsigned int)min(i, 0xFFFFFFFFull));
+    }
+    len[i] = l;
+}
+
+__global__ void __launch_bounds__(256) decode_copy_kernel(const uint32_t *__restrict__ tokens, unsigned long long n,
+                                                         const uint32_t *__restrict__ tok_boff, uint32_t n_ids,
+                                                         const uint8_t *__restrict__ blob,
+                                                         const unsigned long long *__restrict__ base,
+                                                         uint8_t *__restrict__ out) {
+    unsigned long long i = blockIdx.x * 256ull + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t t = tokens[i];
+    if (t >= n_ids) return;
+    const uint32_t b0 = __ldg(tok_boff + t), b1 = __ldg(tok_boff + t + 1);
+    uint8_t *dst = out + base[i];
+    for (uint32_t k = b0; k < b1; k++) *dst++ = __ldg(blob + k);
+}
+
+__global__ void decode_doc_off_kernel(const unsigned long long *__restrict__ tok_off, unsigned long long n_docs,
+                                      const unsigned long long *__restrict__ base, unsigned long long *byte_off) {
+    unsigned long long d = blockIdx.x * 256ull + threadIdx.x;
+    if (d <= n_docs) byte_off[d] = base[tok_off[d]];
+}
+
+// --------------------------------------------------------------------------------------------
 // host side: engine
 // --------------------------------------------------------------------------------------------
 namespace {
@@ -1102,6 +1142,7 @@ struct b200bpe {
     U4 *d_pair_tab = nullptr, *d_piece_tab = nullptr, *d_long_tab = nullptr;
     uint8_t *d_long_blob = nullptr;
     uint16_t *d_uc1 = nullptr; uint8_t *d_uc2 = nullptr, *d_ascii = nullptr;
+    uint32_t *d_tok_boff = nullptr; uint8_t *d_tok_blob = nullptr; uint32_t n_ids = 0;   // decode: id -> bytes
     DevTables T; UcTables uc;
     uint64_t table_bytes[4] = {0, 0, 0, 0};
     static const int N_SLOTS = 3;
@@ -1174,6 +1215,26 @@ extern "C" int b200bpe_create(const uint8_t *tok_bytes, const uint64_t *tok_off,
     if (e == cudaSuccess) e = upload(&h->d_uc1, UC_STAGE1, sizeof(UC_STAGE1));
     if (e == cudaSuccess) e = upload(&h->d_uc2, UC_STAGE2, sizeof(UC_STAGE2));
     if (e == cudaSuccess) e = upload(&h->d_ascii, ascii, 128);
+    {   // decode tables: byte offsets by token id (mergeable ranks and specials); ids above 2^24 are left out
+        uint32_t max_id = 0; bool any = false;
+        for (auto &kv : H.decoder) if (kv.first < (1u << 24)) { if (kv.first > max_id) max_id = kv.first; any = true; }
+        for (auto &kv : h->special_decoder) if (kv.first < (1u << 24)) { if (kv.first > max_id) max_id = kv.first; any = true; }
+        h->n_ids = any ? max_id + 1 : 0;
+        std::vector<uint32_t> boff((size_t)h->n_ids + 2, 0);
+        std::vector<uint8_t> blob;
+        for (uint32_t id = 0; id < h->n_ids; id++) {
+            boff[id] = (uint32_t)blob.size();
+            const std::string *sp = nullptr;
+            auto it = H.decoder.find(id);
+            if (it != H.decoder.end()) sp = &it->second;
+            else { auto it2 = h->special_decoder.find(id); if (it2 != h->special_decoder.end()) sp = &it2->second; }
+            if (sp) blob.insert(blob.end(), sp->begin(), sp->end());
+        }
+        boff[h->n_ids] = (uint32_t)blob.size(); boff[h->n_ids + 1] = (uint32_t)blob.size();
+        if (blob.empty()) blob.push_back(0);
+        if (e == cudaSuccess) e = upload(&h->d_tok_boff, boff.data(), boff.size() * 4);
+        if (e == cudaSuccess) e = upload(&h->d_tok_blob, blob.data(), blob.size());
+    }
     for (int i = 0; i < b200bpe::N_SLOTS && e == cudaSuccess; i++) e = h->slots[i].init();
     if (const char *cm = getenv("B200BPE_CHUNK_MB")) { long v = atol(cm); if (v >= 1 && v <= 2048) h->chunk_bytes = (size_t)v << 20; }
     if (e != cudaSuccess) { std::string m = cudaGetErrorString(e); delete h; return fail(B200BPE_ECUDA, "table upload: " + m); }
@@ -1195,7 +1256,7 @@ extern "C" void b200bpe_destroy(b200bpe_t *h) {
     if (!h) return;
     cudaSetDevice(h->device);
     cudaFree(h->d_byte_id); cudaFree(h->d_pair2); cudaFree(h->d_pair_tab); cudaFree(h->d_piece_tab);
-    cudaFree(h->d_long_tab); cudaFree(h->d_long_blob); cudaFree(h->d_uc1); cudaFree(h->d_uc2); cudaFree(h->d_ascii);
+    cudaFree(h->d_long_tab); cudaFree(h->d_long_blob); cudaFree(h->d_tok_boff); cudaFree(h->d_tok_blob); cudaFree(h->d_uc1); cudaFree(h->d_uc2); cudaFree(h->d_ascii);
     for (int i = 0; i < b200bpe::N_SLOTS; i++) h->slots[i].destroy();
     for (auto &b : h->pinned_pool) cudaFreeHost(b.p);
     delete h;
@@ -1580,6 +1641,68 @@ extern "C" int b200bpe_decode_bytes(b200bpe_t *h, const uint32_t *tokens, uint64
         k += s->size();
     }
     *out_len = k;
+    return B200BPE_OK;
+}
+
+// Batched CoreBPE::decode_bytes (src/lib.rs:345-358) on the device: tokens of all documents
+// concatenated + per-document token offsets (HOST buffers) -> bytes of all documents concatenated
+// + per-document byte offsets.  The result object reuses b200bpe_result: "tokens" holds the bytes
+// (n_tokens = byte count), "offsets" the byte offsets.
+extern "C" int b200bpe_decode_batch(b200bpe_t *h, const uint32_t *tokens, const uint64_t *tok_off, uint64_t n_docs,
+                                    b200bpe_result_t **out, uint32_t *bad_token) {
+    if (!h || !tok_off || !out) return fail(B200BPE_EINVAL, "null argument");
+    const uint64_t n = tok_off[n_docs];
+    if (n && !tokens) return fail(B200BPE_EINVAL, "null tokens");
+    std::lock_guard<std::mutex> lk(h->mu);
+    CUDA_TRY(cudaSetDevice(h->device));
+    Slot &S = h->slots[0];
+    cudaStream_t st = S.stream;
+    // reuse slot-0 workspace: w_out = tokens, w_sub_count = lengths, w_sub_base = byte base, w_text = bytes out
+    CUDA_TRY(S.w_out.ensure((size_t)n + 4)); CUDA_TRY(S.w_sub_count.ensure((size_t)n + 4));
+    CUDA_TRY(S.w_sub_base.ensure((size_t)n + 4)); CUDA_TRY(S.w_scan_part.ensure((size_t)(n / SCAN_ITEMS) + 4));
+    CUDA_TRY(S.w_docoff.ensure((size_t)n_docs + 2)); CUDA_TRY(S.w_tokoff.ensure((size_t)n_docs + 2));
+    CUDA_TRY(cudaMemsetAsync(S.d_ctr, 0, sizeof(Counters), st));
+    CUDA_TRY(cudaMemsetAsync(&S.d_ctr->ticket, 0xFF, sizeof(unsigned int), st));
+    CUDA_TRY(cudaEventRecord(S.ev[0], st));
+    if (n) CUDA_TRY(cudaMemcpyAsync(S.w_out.p, tokens, n * 4, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(S.w_docoff.p, tok_off, (n_docs + 1) * 8, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaEventRecord(S.ev[1], st));
+    const long long nn = (long long)n;
+    const long long nb = (nn + SCAN_ITEMS - 1) / SCAN_ITEMS;
+    if (n) decode_len_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(S.w_out.p, n, h->d_tok_boff, h->n_ids, S.w_sub_count.p, S.d_ctr);
+    if (nb) scan_partial_kernel<<<(unsigned)nb, 256, 0, st>>>(S.w_sub_count.p, nn, S.w_scan_part.p);
+    scan_top_kernel<<<1, 1024, 0, st>>>(S.w_scan_part.p, nb, S.d_ctr);
+    if (nb) scan_final_kernel<<<(unsigned)nb, 256, 0, st>>>(S.w_sub_count.p, nn, S.w_scan_part.p, S.w_sub_base.p, S.d_ctr);
+    else CUDA_TRY(cudaMemsetAsync(S.w_sub_base.p, 0, 8, st));
+    CUDA_TRY(cudaMemcpyAsync(S.h_ctr, S.d_ctr, sizeof(Counters), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    if (S.h_ctr->err & ERR_BADTOKEN) {
+        const uint32_t t = tokens[S.h_ctr->ticket];
+        if (bad_token) *bad_token = t;
+        return fail(B200BPE_EKEY, "Invalid token for decoding: " + std::to_string(t));
+    }
+    const uint64_t n_out = S.h_ctr->total_tokens;
+    CUDA_TRY(S.w_text.ensure((size_t)n_out + 64));
+    if (n) decode_copy_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(S.w_out.p, n, h->d_tok_boff, h->n_ids, h->d_tok_blob,
+                                                                        S.w_sub_base.p, S.w_text.p);
+    decode_doc_off_kernel<<<(unsigned)((n_docs + 1 + 255) / 256), 256, 0, st>>>(S.w_docoff.p, n_docs, S.w_sub_base.p, S.w_tokoff.p);
+    CUDA_TRY(cudaEventRecord(S.ev[2], st));
+    b200bpe_result *r = new b200bpe_result();
+    r->owner = h; r->n_docs = n_docs; r->n_tokens = n_out;
+    r->off = h->take_pinned((size_t)(n_docs + 1) * 8);
+    r->tok = h->take_pinned((size_t)n_out + 16);
+    if (!r->off.p || !r->tok.p) { h->give_pinned(r->tok); h->give_pinned(r->off); delete r; return fail(B200BPE_ECUDA, "pinned allocation failed"); }
+    CUDA_TRY(cudaMemcpyAsync(r->off.p, S.w_tokoff.p, (n_docs + 1) * 8, cudaMemcpyDeviceToHost, st));
+    if (n_out) CUDA_TRY(cudaMemcpyAsync(r->tok.p, S.w_text.p, n_out, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaEventRecord(S.ev[3], st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    CUDA_TRY(cudaGetLastError());
+    memset(h->last_ms, 0, sizeof(h->last_ms));
+    cudaEventElapsedTime(&h->last_ms[5], S.ev[0], S.ev[1]);
+    cudaEventElapsedTime(&h->last_ms[4], S.ev[1], S.ev[2]);
+    cudaEventElapsedTime(&h->last_ms[6], S.ev[2], S.ev[3]);
+    h->last_launches = 6;
+    *out = r;
     return B200BPE_OK;
 }
 
