@@ -59,6 +59,8 @@ struct Counters {            // device-resident, zeroed per call
     unsigned int giant_head;
     unsigned int n_giant;
     unsigned int n_big;
+    unsigned int n_miss;
+    unsigned long long miss_bytes;
     unsigned int ticket;
     unsigned int err;
     unsigned long long total_tokens;
@@ -625,61 +627,66 @@ __global__ void __launch_bounds__(GIANT_THREADS) giant_piece_kernel(const uint8_
 }
 
 // --------------------------------------------------------------------------------------------
-// kernel 4: encode.  One WARP per 1 KiB sub-tile (32 lanes x 32-byte spans), no block barriers:
-// a warp that is waiting on L2 probes or merging its misses never stalls its neighbours.
-// The warp leaves its tokens compacted in a fixed-stride scratch region plus (count, flags);
-// a scan over the counts and a gather kernel (kernel 6) place them -- kernel boundaries do the
-// ordering, there is no look-back chain and no ticket counter.
+// kernels 4-6: encode = probe -> merge the misses -> (scan) -> gather.
+//
+// probe_kernel   one WARP per 1 KiB sub-tile: stage text + piece starts in shared memory, compact
+//                the piece starts into a list (all 32 lanes busy whatever the distribution), probe
+//                every piece of <= 16 bytes in the piece table (src/lib.rs:367-368), two probes in
+//                flight per lane.  One 32-bit slot per PIECE goes to `ptok` (token id, or a tagged
+//                reference to the miss queue / the long-piece queue); misses are appended to a
+//                global queue.  Small footprint (4.4 KB smem/warp) => many warps hide the L2 latency.
+// miss_kernel    the ~5 % of pieces that are not tokens, DENSE: one piece per lane, 32 per warp,
+//                all lanes walking one convergent instruction stream (merge_short_conv), the
+//                literal min-rank loop of _byte_pair_merge (src/lib.rs:140-196).
+// gather_kernel  one warp per sub-tile: per-piece token counts -> warp scan -> tokens and
+//                per-document offsets written at their final position.
+// Kernel boundaries do the ordering; there is no look-back chain and no ticket counter.
 // --------------------------------------------------------------------------------------------
+static const uint32_t PT_MISS = 0x40000000u, PT_LONG = 0x80000000u, PT_KIND = 0xC0000000u, PT_PAYLOAD = 0x3FFFFFFFu;
+static const uint32_t PT_EMPTY = 0xFFFFFFFFu;             // zero-token slot (only on error paths)
+
+struct MissQ {                // queue of pieces (2..16 bytes) that are not tokens themselves
+    uint32_t *pos;            // byte offset of the piece
+    uint32_t *roff;           // offset of its result region in mres (sum of lengths => tokens always fit)
+    uint8_t *len;
+    uint8_t *cnt;             // tokens produced (written by miss_kernel)
+};
+
 struct TileParams {
     const uint8_t *text; long long n_bytes; long long n_words; long long n_sub;
     const uint32_t *pbits; const uint32_t *dbits; const uint32_t *span_first_doc;
     const unsigned long long *doc_off; unsigned long long n_docs;
     LongQ q; const uint32_t *lidx; const uint32_t *ltok;
-    uint32_t *scratch;            // [n_sub][SUB_CAP] short-piece tokens of each sub-tile, compacted in byte order
-    uint32_t *tbits;              // token-start bitmask words (short pieces), one per span
-    uint32_t *sub_count;          // [n_sub] tokens emitted by the sub-tile (short + long)
-    uint32_t *sub_flags;          // [n_sub] bit0: has long piece, bit1: has document start, bits 8..: straddling tokens
-    unsigned long long *sub_base; // [n_sub+1] exclusive prefix of sub_count (kernel 5)
+    uint32_t *ptok;               // [n_sub][SUB_BYTES] one slot per piece, in piece order
+    MissQ mq; uint32_t *mres;     // miss queue and its token results
+    uint32_t *sub_count;          // [n_sub] tokens emitted by the sub-tile
+    unsigned long long *sub_base; // [n_sub+1] exclusive prefix of sub_count
     uint32_t *out; unsigned long long *tok_off;
     unsigned long long *big_dst, *big_src; uint32_t *big_n;   // token copies too large for one warp (kernel 7)
     Counters *ctr;
 };
 
 static const int ENC_WARPS = 4;                          // warps per block
-static const int SUB_BYTES = 1024;                       // bytes per warp sub-tile
-static const int SUB_CAP = SUB_BYTES + SHORT_MAX;        // scratch slots per sub-tile (tokens <= bytes)
+static const int SUB_BYTES = 1024;                       // bytes per warp sub-tile (also: max pieces per sub-tile)
 
-struct WarpSmem {
+struct ProbeSmem {
     __align__(16) uint8_t text[SUB_BYTES + 32];
     uint32_t p[34];
-    uint32_t tmask[33];
     uint32_t nmiss;
-    uint32_t tok[SUB_BYTES + SHORT_MAX];
-    uint16_t miss[SUB_BYTES / 2];
-    union {                            // phase A uses plist, phase B (after a __syncwarp) the merge state
-        uint16_t plist[SUB_BYTES + 2]; // piece start offsets of the sub-tile, in order, + end sentinel
-        struct {
-            uint32_t mid[SHORT_MAX * 16];  // merge state of up to 16 concurrently merged pieces: [part][slot]
-            uint32_t mrk[SHORT_MAX * 16];
-        };
-    };
+    uint16_t plist[SUB_BYTES + 2];     // piece start offsets of the sub-tile, in order, + end sentinel
+    uint16_t miss[SUB_BYTES / 2];      // piece indices (into plist) of the misses
 };
 
-struct SmemCol16 {                     // one slot's column of a [SHORT_MAX][16] shared array
-    uint32_t *base;
-    __device__ __forceinline__ uint32_t &operator[](int j) const { return base[j * 16]; }
-};
-
-__global__ void __launch_bounds__(ENC_WARPS * 32) encode_tiles_kernel(TileParams p, DevTables T) {
-    __shared__ WarpSmem smem[ENC_WARPS];
-    WarpSmem &S = smem[threadIdx.x >> 5];
+__global__ void __launch_bounds__(ENC_WARPS * 32) probe_kernel(TileParams p, DevTables T) {
+    __shared__ ProbeSmem smem[ENC_WARPS];
+    ProbeSmem &S = smem[threadIdx.x >> 5];
     const int lane = threadIdx.x & 31;
     const long long safe_end = p.n_bytes & ~15ll;
     const long long sub = (long long)blockIdx.x * ENC_WARPS + (threadIdx.x >> 5);
     if (sub >= p.n_sub) return;
     const long long sub_byte = sub * SUB_BYTES;
     const long long gw = sub * 32 + lane;              // this lane's bitmask word
+    uint32_t *const slot = p.ptok + sub * SUB_BYTES;
 
     // ---- stage text (1 KiB + 32 B tail) and piece-start words ----------------------------
     for (int v = lane; v < (SUB_BYTES + 32) / 16; v += 32) {
@@ -697,12 +704,11 @@ __global__ void __launch_bounds__(ENC_WARPS * 32) encode_tiles_kernel(TileParams
     {
         S.p[lane] = (gw < p.n_words) ? __ldg(p.pbits + gw) : 0u;
         if (lane < 2) { long long w2 = sub * 32 + 32 + lane; S.p[32 + lane] = (w2 < p.n_words) ? __ldg(p.pbits + w2) : 0u; }
-        if (lane == 0) { S.tmask[32] = 0; S.nmiss = 0; }
+        if (lane == 0) S.nmiss = 0;
     }
     __syncwarp();
 
-    // ---- piece list: compact the piece starts of the sub-tile so that the probe loop below runs
-    //      with all 32 lanes busy whatever the distribution of pieces over the spans ----------
+    // ---- piece list ------------------------------------------------------------------------
     uint32_t pv = S.p[lane];
     {
         const long long span0 = sub_byte + lane * 32;
@@ -728,27 +734,25 @@ __global__ void __launch_bounds__(ENC_WARPS * 32) encode_tiles_kernel(TileParams
             const long long tail = p.n_bytes - sub_byte;           // text ends inside this sub-tile?
             S.plist[np] = (uint16_t)(tail <= SUB_BYTES ? tail : (nx ? SUB_BYTES + __ffs(nx) - 1 : SUB_BYTES + 32));
         }
-        S.tmask[lane] = pv;                                // every piece start is a token start until proven otherwise
     }
     __syncwarp();
 
-    // ---- phase A: whole-piece probe (src/lib.rs:367-368).  Two pieces per lane per iteration so that
-    //      two table probes are in flight per lane (the loop is bound by L2 latency, not by issue) ----
-    uint32_t cl = 0;                                       // tokens of long pieces met by this lane
+    // ---- whole-piece probe, two pieces per lane per iteration --------------------------------
+    uint32_t cnt = 0;                                      // tokens known so far (hits, single bytes, long pieces)
     auto prep = [&](uint32_t i, int &off, int &len, uint64_t &k0, uint64_t &k1) -> int {
-        // returns 0: nothing to probe (handled here), 1: probe needed
         if (i >= np) return 0;
         off = S.plist[i];
         len = (int)S.plist[i + 1] - off;
-        if (len > SHORT_MAX) {                             // long path: precomputed by long_piece_kernel
-            atomicAnd(&S.tmask[off >> 5], ~(1u << (off & 31)));
-            cl += p.q.ntok[p.lidx[(sub_byte + off) >> 4]];
+        if (len > SHORT_MAX) {                             // long path: precomputed by long_piece / giant_piece
+            const uint32_t qi = p.lidx[(sub_byte + off) >> 4];
+            cnt += p.q.ntok[qi];
+            slot[i] = PT_LONG | qi;
             return 0;
         }
         if (len == 1) {
             const uint32_t id = __ldg(T.byte_id + S.text[off]);
-            if (id >= PSEUDO_BASE) atomicOr(&p.ctr->err, ERR_NOBYTE);
-            S.tok[off] = id;
+            if (id >= PSEUDO_BASE) { atomicOr(&p.ctr->err, ERR_NOBYTE); slot[i] = PT_EMPTY; }
+            else { slot[i] = id; cnt++; }
             return 0;
         }
         const uint32_t *wp = reinterpret_cast<const uint32_t *>(S.text) + (off >> 2);
@@ -762,7 +766,7 @@ __global__ void __launch_bounds__(ENC_WARPS * 32) encode_tiles_kernel(TileParams
         k0 = (((uint64_t)a1 << 32) | a0) & mk0; k1 = (((uint64_t)a3 << 32) | a2) & mk1;
         return 1;
     };
-    auto finish = [&](int off, int len, uint64_t k0, uint64_t k1, uint32_t s, U4 m, U4 k) {
+    auto finish = [&](uint32_t i, int len, uint64_t k0, uint64_t k1, uint32_t s, U4 m, U4 k) {
         uint32_t r = RANK_MAX;
         for (;;) {                                         // continue the linear probe from the prefetched slot
             if (m.x == 0) break;
@@ -771,12 +775,8 @@ __global__ void __launch_bounds__(ENC_WARPS * 32) encode_tiles_kernel(TileParams
             s = (s + 1) & T.piece_mask;
             m = B2_LDG_U4(T.piece_tab + 2 * s + 1); k = B2_LDG_U4(T.piece_tab + 2 * s);
         }
-        if (r != RANK_MAX) S.tok[off] = r;
-        else {
-            atomicAnd(&S.tmask[off >> 5], ~(1u << (off & 31)));
-            const uint32_t slot = atomicAdd(&S.nmiss, 1u);
-            S.miss[slot] = (uint16_t)(off | ((len - 1) << 12));
-        }
+        if (r != RANK_MAX) { slot[i] = r; cnt++; }
+        else S.miss[atomicAdd(&S.nmiss, 1u)] = (uint16_t)i;
     };
     for (uint32_t i = lane; i < np; i += 64) {
         int offA = 0, lenA = 0, offB = 0, lenB = 0;
@@ -787,76 +787,110 @@ __global__ void __launch_bounds__(ENC_WARPS * 32) encode_tiles_kernel(TileParams
         U4 mA = {0, 0, 0, 0}, kA = {0, 0, 0, 0}, mB = {0, 0, 0, 0}, kB = {0, 0, 0, 0};
         if (needA) { sA = (uint32_t)piece_hash(a0, a1, (uint32_t)lenA) & T.piece_mask; mA = B2_LDG_U4(T.piece_tab + 2 * sA + 1); kA = B2_LDG_U4(T.piece_tab + 2 * sA); }
         if (needB) { sB = (uint32_t)piece_hash(b0, b1, (uint32_t)lenB) & T.piece_mask; mB = B2_LDG_U4(T.piece_tab + 2 * sB + 1); kB = B2_LDG_U4(T.piece_tab + 2 * sB); }
-        if (needA) finish(offA, lenA, a0, a1, sA, mA, kA);
-        if (needB) finish(offB, lenB, b0, b1, sB, mB, kB);
+        if (needA) finish(i, lenA, a0, a1, sA, mA, kA);
+        if (needB) finish(i + 32, lenB, b0, b1, sB, mB, kB);
     }
     __syncwarp();
 
-    // ---- phase B: exact merge of the pieces that missed; lanes 0..15 take one piece each per pass
-    //      and walk one convergent instruction stream (merge_short_conv) --------------------------
-    {
-        const uint32_t nmiss = S.nmiss;
-        SmemCol16 id{S.mid + (lane & 15)}, rk{S.mrk + (lane & 15)};
-        if (lane < 16) {
-            for (uint32_t i0 = 0; i0 < nmiss; i0 += 16) {
-                const uint32_t i = i0 + lane;
-                const bool have = i < nmiss;
-                const uint32_t e = have ? S.miss[i] : 0u;
-                const int off = e & 0xFFF, len = have ? (int)(e >> 12) + 1 : 0;
-                int n_max = len;
+    // ---- misses -> global queue (one atomic per sub-tile), result space = sum of their lengths ----
+    const uint32_t nmiss = S.nmiss;
+    if (nmiss) {
+        uint32_t qbase = 0, rbase = 0, run = 0;
+        for (uint32_t k0 = 0; k0 < nmiss; k0 += 32) {      // total length first
+            const uint32_t k = k0 + lane;
+            uint32_t len = 0;
+            if (k < nmiss) { const uint32_t i = S.miss[k]; len = (uint32_t)S.plist[i + 1] - S.plist[i]; }
 #pragma unroll
-                for (int o = 8; o; o >>= 1) n_max = max(n_max, __shfl_xor_sync(0x0000FFFFu, n_max, o));
-                const uint8_t *pc = S.text + off;
-                const uint32_t mask = merge_short_conv(T, [&](int j) { return (uint32_t)pc[j]; }, len, n_max,
-                                                       0x0000FFFFu, id, rk);
-                if (have) {
-                    bool bad = false;
-                    for (uint32_t mm = mask; mm;) {
-                        int j = __ffs(mm) - 1; mm &= mm - 1;
-                        uint32_t x = id[j];
-                        bad |= x >= PSEUDO_BASE;
-                        S.tok[off + j] = x;
-                    }
-                    if (bad) atomicOr(&p.ctr->err, ERR_NOBYTE);
-                    const int wi = off >> 5, sh = off & 31;
-                    atomicOr(&S.tmask[wi], mask << sh);
-                    if (sh + len > 32) atomicOr(&S.tmask[wi + 1], mask >> (32 - sh));
-                }
+            for (int o = 16; o; o >>= 1) len += __shfl_xor_sync(0xFFFFFFFFu, len, o);
+            run += len;
+        }
+        if (lane == 0) {
+            qbase = atomicAdd(&p.ctr->n_miss, nmiss);
+            rbase = (uint32_t)atomicAdd(&p.ctr->miss_bytes, (unsigned long long)run);
+        }
+        qbase = __shfl_sync(0xFFFFFFFFu, qbase, 0); rbase = __shfl_sync(0xFFFFFFFFu, rbase, 0);
+        run = 0;
+        for (uint32_t k0 = 0; k0 < nmiss; k0 += 32) {
+            const uint32_t k = k0 + lane;
+            uint32_t i = 0, off = 0, len = 0;
+            if (k < nmiss) { i = S.miss[k]; off = S.plist[i]; len = (uint32_t)S.plist[i + 1] - off; }
+            uint32_t inc = len;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync(0xFFFFFFFFu, inc, o); if (lane >= o) inc += y; }
+            if (k < nmiss) {
+                const uint32_t qi = qbase + k;
+                p.mq.pos[qi] = (uint32_t)(sub_byte + off); p.mq.len[qi] = (uint8_t)len; p.mq.roff[qi] = rbase + run + inc - len;
+                slot[i] = PT_MISS | qi;
             }
+            run += __shfl_sync(0xFFFFFFFFu, inc, 31);
         }
     }
-    __syncwarp();
-
-    // ---- phase C: compact the short-piece tokens into the scratch region, publish counts ----
-    const uint32_t tm = S.tmask[lane];
-    const uint32_t extra = (lane == 31) ? S.tmask[32] : 0u;
-    const uint32_t cs = __popc(tm) + __popc(extra);
-    uint32_t incl = cs, tot_long = cl;
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        uint32_t y = __shfl_up_sync(0xFFFFFFFFu, incl, o);
-        if (lane >= o) incl += y;
-    }
-#pragma unroll
-    for (int o = 16; o; o >>= 1) tot_long += __shfl_xor_sync(0xFFFFFFFFu, tot_long, o);
-    const uint32_t tot_short = __shfl_sync(0xFFFFFFFFu, incl, 31);
-    {
-        uint32_t *dst = p.scratch + sub * SUB_CAP + (incl - cs);
-        for (uint32_t mm = tm; mm;) { int j = __ffs(mm) - 1; mm &= mm - 1; *dst++ = S.tok[lane * 32 + j]; }
-        for (uint32_t mm = extra; mm;) { int j = __ffs(mm) - 1; mm &= mm - 1; *dst++ = S.tok[SUB_BYTES + j]; }
-    }
-    if (gw < p.n_words) p.tbits[gw] = tm;
-    const uint32_t dm = (gw < p.n_words) ? __ldg(p.dbits + gw) : 0u;
-    const uint32_t any_long = tot_long, any_doc = __ballot_sync(0xFFFFFFFFu, dm != 0);
-    if (lane == 31) {
-        p.sub_count[sub] = tot_short + tot_long;
-        p.sub_flags[sub] = (any_long ? 1u : 0u) | (any_doc ? 2u : 0u) | ((uint32_t)__popc(extra) << 8);
-    }
+    for (int o = 16; o; o >>= 1) cnt += __shfl_xor_sync(0xFFFFFFFFu, cnt, o);
+    if (lane == 0) p.sub_count[sub] = cnt;                 // miss_kernel adds the tokens of the misses
 }
 
 // --------------------------------------------------------------------------------------------
-// kernel 5: exclusive scan of the per-sub-tile token counts (single block; n_sub ~ N / 1024)
+// kernel 5: the misses, one piece per lane
 // --------------------------------------------------------------------------------------------
+static const int MISS_WARPS = 4;
+
+struct MissSmem {
+    uint32_t id[SHORT_MAX * 32];       // [part][lane]
+    uint32_t rk[SHORT_MAX * 32];
+    uint32_t bytes[4 * 32];            // [word][lane]: the piece bytes, little-endian
+};
+struct SmemCol32 {
+    uint32_t *base;
+    __device__ __forceinline__ uint32_t &operator[](int j) const { return base[j * 32]; }
+};
+
+__global__ void __launch_bounds__(MISS_WARPS * 32) miss_kernel(TileParams p, DevTables T) {
+    __shared__ MissSmem smem[MISS_WARPS];
+    MissSmem &S = smem[threadIdx.x >> 5];
+    const int lane = threadIdx.x & 31;
+    const uint32_t n_miss = p.ctr->n_miss;
+    const uint32_t stride = gridDim.x * MISS_WARPS * 32;
+    for (uint32_t q0 = (blockIdx.x * MISS_WARPS + (threadIdx.x >> 5)) * 32; q0 < n_miss; q0 += stride) {
+        const uint32_t qi = q0 + lane;
+        const bool have = qi < n_miss;
+        uint32_t pos = 0; int len = 0;
+        if (have) { pos = p.mq.pos[qi]; len = p.mq.len[qi]; }
+        {   // 16 bytes at an arbitrary offset: five aligned words + funnel shifts (text is padded)
+            const uint32_t *wp = reinterpret_cast<const uint32_t *>(p.text + (pos & ~3u));
+            const int sh = (pos & 3) * 8;
+            uint32_t w[5] = {0, 0, 0, 0, 0};
+            if (have) {
+#pragma unroll
+                for (int k = 0; k < 5; k++) w[k] = ((long long)(pos & ~3u) + 4 * k < p.n_bytes) ? __ldg(wp + k) : 0u;
+            }
+#pragma unroll
+            for (int k = 0; k < 4; k++) S.bytes[k * 32 + lane] = __funnelshift_r(w[k], w[k + 1], sh);
+        }
+        int n_max = len;
+#pragma unroll
+        for (int o = 16; o; o >>= 1) n_max = max(n_max, __shfl_xor_sync(0xFFFFFFFFu, n_max, o));
+        SmemCol32 id{S.id + lane}, rk{S.rk + lane};
+        const uint32_t *bw = S.bytes + lane;
+        const uint32_t mask = merge_short_conv(
+            T, [&](int j) { return (bw[(j >> 2) * 32] >> (8 * (j & 3))) & 0xFFu; }, len, n_max, 0xFFFFFFFFu, id, rk);
+        if (have) {
+            uint32_t *dst = p.mres + p.mq.roff[qi];
+            uint32_t c = 0; bool bad = false;
+            for (uint32_t mm = mask; mm;) {
+                const int j = __ffs(mm) - 1; mm &= mm - 1;
+                const uint32_t x = id[j];
+                bad |= x >= PSEUDO_BASE;
+                dst[c++] = x;
+            }
+            if (bad) atomicOr(&p.ctr->err, ERR_NOBYTE);
+            p.mq.cnt[qi] = (uint8_t)c;
+            atomicAdd(&p.sub_count[pos >> 10], c);
+        }
+        __syncwarp();
+    }
+}
+
 static const int SCAN_ITEMS = 4096;                 // counts per block of the two-level scan
 
 __global__ void __launch_bounds__(256) scan_partial_kernel(const uint32_t *__restrict__ cnt, long long n,
@@ -921,71 +955,77 @@ __global__ void add_offset_kernel(unsigned long long *a, unsigned long long n, l
 }
 
 // --------------------------------------------------------------------------------------------
-// kernel 6: gather.  One warp per sub-tile: straight coalesced copy when the sub-tile has neither
-// long pieces nor document starts, otherwise the per-span walk that splices long-piece tokens in
-// and writes the per-document token offsets.
+// kernel 6: gather.  One warp per sub-tile; each lane walks the pieces that start in its 32-byte
+// span (they are consecutive slots of ptok): count, warp scan, then write tokens and the
+// per-document token offsets at their final position.
 // --------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) gather_kernel(TileParams p) {
     const int lane = threadIdx.x & 31;
     const long long sub = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
     if (sub >= p.n_sub) return;
     const unsigned long long base = p.sub_base[sub];
-    const uint32_t flags = p.sub_flags[sub];
-    const uint32_t *src = p.scratch + sub * SUB_CAP;
-    if ((flags & 3u) == 0) {
-        const uint32_t n = p.sub_count[sub];
-        for (uint32_t i = lane; i < n; i += 32) p.out[base + i] = src[i];
-        return;
-    }
+    const uint32_t *slot = p.ptok + sub * SUB_BYTES;
     const long long sub_byte = sub * SUB_BYTES;
     const long long gw = sub * 32 + lane;
     const bool in = gw < p.n_words;
-    const uint32_t tm = in ? p.tbits[gw] : 0u;
-    const uint32_t dm = in ? p.dbits[gw] : 0u;
-    const uint32_t pw = in ? p.pbits[gw] : 0u;
-    const uint32_t pw1 = (gw + 1 < p.n_words) ? p.pbits[gw + 1] : 0u;
-    const uint64_t ahead = ((uint64_t)pw1 << 32) | pw;
-    uint32_t lm = 0;
-    for (uint32_t m = pw; m;) {
-        const int j = __ffs(m) - 1; m &= m - 1;
-        if (sub_byte + lane * 32 + j >= p.n_bytes) break;
-        if (((uint32_t)((ahead >> j) >> 1) & 0xFFFFu) == 0) lm |= 1u << j;
+    const uint32_t dm = in ? __ldg(p.dbits + gw) : 0u;
+    uint32_t pv = in ? __ldg(p.pbits + gw) : 0u;
+    {
+        const long long span0 = sub_byte + lane * 32;
+        if (span0 + 32 > p.n_bytes) {
+            const long long keep = p.n_bytes - span0;
+            pv = keep <= 0 ? 0u : (pv & ((1u << keep) - 1u));
+        }
     }
-    const uint32_t n_extra = (lane == 31) ? (flags >> 8) : 0u;
-    const uint32_t cs = __popc(tm) + n_extra;
-    uint32_t cl = 0;
-    for (uint32_t mm = lm; mm;) {
-        int j = __ffs(mm) - 1; mm &= mm - 1;
-        cl += p.q.ntok[p.lidx[(sub_byte + lane * 32 + j) >> 4]];
-    }
-    uint32_t incl_s = cs, incl_t = cs + cl;
+    const uint32_t c = __popc(pv);
+    uint32_t pinc = c;
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        uint32_t y = __shfl_up_sync(0xFFFFFFFFu, incl_s, o), z = __shfl_up_sync(0xFFFFFFFFu, incl_t, o);
-        if (lane >= o) { incl_s += y; incl_t += z; }
-    }
-    unsigned long long k = base + (incl_t - cs - cl);
-    uint32_t si = incl_s - cs;                                   // index of this lane's first short token in scratch
+    for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync(0xFFFFFFFFu, pinc, o); if (lane >= o) pinc += y; }
+    const uint32_t pi0 = pinc - c;                           // index of this lane's first piece
+    auto count_of = [&](uint32_t v) -> uint32_t {
+        if (v == PT_EMPTY) return 0u;
+        const uint32_t kind = v & PT_KIND;
+        if (kind == 0) return 1u;
+        if (kind == PT_MISS) return p.mq.cnt[v & PT_PAYLOAD];
+        return p.q.ntok[v & PT_PAYLOAD];
+    };
+    uint32_t t = 0;
+    for (uint32_t k = 0; k < c; k++) t += count_of(slot[pi0 + k]);
+    uint32_t tinc = t;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync(0xFFFFFFFFu, tinc, o); if (lane >= o) tinc += y; }
+    unsigned long long k = base + (tinc - t);
     unsigned long long big_dst = 0, big_src = 0; uint32_t big_n = 0;
-    unsigned long long d = dm ? (unsigned long long)p.span_first_doc[gw] : 0ull;
-    uint32_t walk = tm | lm | dm;
+    unsigned long long d = dm ? (unsigned long long)__ldg(p.span_first_doc + gw) : 0ull;
+    uint32_t pi = pi0;
+    uint32_t walk = pv | dm;
     while (walk) {
         const int j = __ffs(walk) - 1; walk &= walk - 1;
         const long long pos = sub_byte + lane * 32 + j;
         if ((dm >> j) & 1u) {
             while (d <= p.n_docs && p.doc_off[d] == (unsigned long long)pos) { p.tok_off[d] = k; d++; }
         }
-        if ((tm >> j) & 1u) { p.out[k++] = src[si++]; }
-        else if ((lm >> j) & 1u) {
-            const uint32_t qi = p.lidx[pos >> 4];
-            const uint32_t nt = p.q.ntok[qi];
-            const unsigned long long lsrc = p.q.off[qi];
-            if (nt <= 32) { for (uint32_t x = 0; x < nt; x++) p.out[k + x] = p.ltok[lsrc + x]; }
-            else { big_dst = k; big_src = lsrc; big_n = nt; }   // > 32 tokens => > 32 bytes: at most one per span
-            k += nt;
+        if ((pv >> j) & 1u) {
+            const uint32_t v = slot[pi++];
+            if (v == PT_EMPTY) continue;
+            const uint32_t kind = v & PT_KIND;
+            if (kind == 0) { p.out[k++] = v; }
+            else if (kind == PT_MISS) {
+                const uint32_t qi = v & PT_PAYLOAD;
+                const uint32_t n = p.mq.cnt[qi];
+                const uint32_t *src = p.mres + p.mq.roff[qi];
+                for (uint32_t x = 0; x < n; x++) p.out[k + x] = src[x];
+                k += n;
+            } else {
+                const uint32_t qi = v & PT_PAYLOAD;
+                const uint32_t nt = p.q.ntok[qi];
+                const unsigned long long lsrc = p.q.off[qi];
+                if (nt <= 32) { for (uint32_t x = 0; x < nt; x++) p.out[k + x] = p.ltok[lsrc + x]; }
+                else { big_dst = k; big_src = lsrc; big_n = nt; }   // > 32 tokens => > 32 bytes: at most one per span
+                k += nt;
+            }
         }
     }
-    for (uint32_t x = 0; x < n_extra; x++) p.out[k++] = src[si++];
     for (uint32_t pending = __ballot_sync(0xFFFFFFFFu, big_n != 0); pending; pending &= pending - 1) {
         const int src_lane = __ffs(pending) - 1;
         const unsigned long long dst = __shfl_sync(0xFFFFFFFFu, big_dst, src_lane);
@@ -1089,7 +1129,7 @@ struct PinnedBuf {
 // three slots in flight (H2D of chunk c+1, kernels of chunk c, D2H of chunk c-1).
 struct Slot {
     DevBuf<uint8_t> w_text; DevBuf<unsigned long long> w_docoff, w_tokoff, w_sub_base;
-    DevBuf<uint32_t> w_scratch, w_tbits, w_sub_count, w_sub_flags;
+    DevBuf<uint32_t> w_ptok, w_mres, w_mq_pos, w_mq_roff, w_sub_count; DevBuf<uint8_t> w_mq_len, w_mq_cnt;
     DevBuf<uint32_t> w_dbits, w_pbits, w_psum, w_sfd, w_lidx, w_out, w_ltok;
     DevBuf<unsigned long long> w_lq_start, w_lq_off; DevBuf<unsigned int> w_lq_len, w_lq_ntok, w_lq_giant, w_big_n; DevBuf<unsigned long long> w_big_dst, w_big_src, w_scan_part;
     DevBuf<uint32_t> w_idA, w_rkA, w_idB, w_rkB, w_aux1, w_aux2; DevBuf<uint8_t> w_flag;
@@ -1110,7 +1150,8 @@ struct Slot {
     }
     void destroy() {
         w_text.release(); w_docoff.release(); w_tokoff.release(); w_sub_base.release();
-        w_scratch.release(); w_tbits.release(); w_sub_count.release(); w_sub_flags.release();
+        w_ptok.release(); w_mres.release(); w_mq_pos.release(); w_mq_roff.release(); w_sub_count.release();
+        w_mq_len.release(); w_mq_cnt.release();
         w_dbits.release(); w_pbits.release(); w_psum.release(); w_sfd.release(); w_lidx.release(); w_out.release(); w_ltok.release();
         w_lq_start.release(); w_lq_off.release(); w_lq_len.release(); w_lq_ntok.release(); w_lq_giant.release(); w_big_n.release(); w_big_dst.release(); w_big_src.release(); w_scan_part.release();
         w_idA.release(); w_rkA.release(); w_idB.release(); w_rkB.release(); w_aux1.release(); w_aux2.release();
@@ -1283,9 +1324,14 @@ static int run_pipeline(b200bpe *h, Slot &S, const uint8_t *d_text, uint64_t n_b
     CUDA_TRY(S.w_sfd.ensure((size_t)n_words + 4));
     CUDA_TRY(S.w_sub_base.ensure((size_t)n_tiles + 2));
     CUDA_TRY(S.w_scan_part.ensure((size_t)(n_tiles / SCAN_ITEMS) + 4));
-    CUDA_TRY(S.w_sub_count.ensure((size_t)n_tiles + 2)); CUDA_TRY(S.w_sub_flags.ensure((size_t)n_tiles + 2));
-    CUDA_TRY(S.w_tbits.ensure((size_t)n_words + 4));
-    CUDA_TRY(S.w_scratch.ensure((size_t)n_tiles * SUB_CAP + 64));
+    CUDA_TRY(S.w_sub_count.ensure((size_t)n_tiles + 2));
+    CUDA_TRY(S.w_ptok.ensure((size_t)n_tiles * SUB_BYTES + 64));
+    {   // a miss has >= 2 bytes; its tokens never outnumber its bytes
+        const size_t mcap = (size_t)(n_bytes / 2) + 64;
+        CUDA_TRY(S.w_mq_pos.ensure(mcap)); CUDA_TRY(S.w_mq_roff.ensure(mcap));
+        CUDA_TRY(S.w_mq_len.ensure(mcap)); CUDA_TRY(S.w_mq_cnt.ensure(mcap));
+        CUDA_TRY(S.w_mres.ensure((size_t)n_bytes + 64));
+    }
     CUDA_TRY(S.w_lidx.ensure((size_t)(n_bytes >> 4) + 4));
     const size_t qcap = (size_t)(n_bytes / (SHORT_MAX + 1)) + 4;
     CUDA_TRY(S.w_lq_start.ensure(qcap)); CUDA_TRY(S.w_lq_off.ensure(qcap));
@@ -1353,11 +1399,13 @@ static int run_pipeline(b200bpe *h, Slot &S, const uint8_t *d_text, uint64_t n_b
         p.text = d_text; p.n_bytes = (long long)n_bytes; p.n_words = n_words; p.n_sub = n_tiles;
         p.pbits = S.w_pbits.p; p.dbits = S.w_dbits.p; p.span_first_doc = S.w_sfd.p;
         p.doc_off = d_doc_off; p.n_docs = n_docs; p.q = q; p.lidx = S.w_lidx.p; p.ltok = S.w_ltok.p;
-        p.scratch = S.w_scratch.p; p.tbits = S.w_tbits.p; p.sub_count = S.w_sub_count.p;
-        p.sub_flags = S.w_sub_flags.p; p.sub_base = S.w_sub_base.p;
+        p.ptok = S.w_ptok.p; p.mres = S.w_mres.p;
+        p.mq = MissQ{S.w_mq_pos.p, S.w_mq_roff.p, S.w_mq_len.p, S.w_mq_cnt.p};
+        p.sub_count = S.w_sub_count.p; p.sub_base = S.w_sub_base.p;
         p.out = d_out; p.tok_off = d_tok_off; p.ctr = S.d_ctr;
         p.big_dst = S.w_big_dst.p; p.big_src = S.w_big_src.p; p.big_n = S.w_big_n.p;
-        encode_tiles_kernel<<<(unsigned)((n_tiles + ENC_WARPS - 1) / ENC_WARPS), ENC_WARPS * 32, 0, st>>>(p, h->T);
+        probe_kernel<<<(unsigned)((n_tiles + ENC_WARPS - 1) / ENC_WARPS), ENC_WARPS * 32, 0, st>>>(p, h->T);
+        miss_kernel<<<148 * 8, MISS_WARPS * 32, 0, st>>>(p, h->T);
         CUDA_TRY(cudaEventRecord(S.ev[7], st));
         {
             const long long nb = (n_tiles + SCAN_ITEMS - 1) / SCAN_ITEMS;
@@ -1367,7 +1415,7 @@ static int run_pipeline(b200bpe *h, Slot &S, const uint8_t *d_text, uint64_t n_b
         }
         gather_kernel<<<(unsigned)((n_tiles + 7) / 8), 256, 0, st>>>(p);
         big_copy_kernel<<<148 * 2, 256, 0, st>>>(p);
-        launches += 6;
+        launches += 7;
     }
     CUDA_TRY(cudaEventRecord(S.ev[4], st));
     CUDA_TRY(cudaMemcpyAsync(S.h_ctr, S.d_ctr, sizeof(Counters), cudaMemcpyDeviceToHost, st));

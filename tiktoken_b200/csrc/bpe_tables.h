@@ -64,7 +64,7 @@ inline int build_tables(const uint8_t *tok_bytes, const uint64_t *tok_off, const
     for (uint32_t i = 0; i < n; i++) {
         uint64_t len = tok_off[i + 1] - tok_off[i];
         if (len == 0) { H.error = "empty token in mergeable_ranks"; return -1; }
-        if (tok_rank[i] >= PSEUDO_BASE) { H.error = "rank too large"; return -1; }
+        if (tok_rank[i] >= (1u << 30)) { H.error = "rank too large (token ids must be < 2^30)"; return -1; }
         std::string s((const char *)tok_bytes + tok_off[i], (size_t)len);
         if (!enc.emplace(s, tok_rank[i]).second) { H.error = "duplicate token bytes"; return -1; }
         if (!H.decoder.emplace(tok_rank[i], s).second) {
