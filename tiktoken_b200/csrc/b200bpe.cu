@@ -61,6 +61,8 @@ struct Counters {            // device-resident, zeroed per call
     unsigned int n_big;
     unsigned int n_miss;
     unsigned long long miss_bytes;
+    unsigned int miss_hist[20];      // misses per piece length (2..16)
+    unsigned int miss_fill[20];      // running fill of each length bucket (miss_sort_kernel)
     unsigned int ticket;
     unsigned int err;
     unsigned long long total_tokens;
@@ -650,6 +652,7 @@ struct MissQ {                // queue of pieces (2..16 bytes) that are not toke
     uint32_t *roff;           // offset of its result region in mres (sum of lengths => tokens always fit)
     uint8_t *len;
     uint8_t *cnt;             // tokens produced (written by miss_kernel)
+    uint32_t *order;          // queue indices sorted by piece length (so that a warp merges pieces of one length)
 };
 
 struct TileParams {
@@ -845,6 +848,54 @@ struct SmemCol32 {
     __device__ __forceinline__ uint32_t &operator[](int j) const { return base[j * 32]; }
 };
 
+// counting sort of the miss queue by piece length (so that a warp merges pieces of one length):
+// per-block histograms -> bucket bases -> scatter.  Only block-local shared-memory atomics and
+// 17 values per block in global memory; no hot global counters.
+static const int SORT_BLOCKS = 148 * 2;
+
+__global__ void __launch_bounds__(256) miss_hist_kernel(TileParams p, unsigned int *block_hist /* [SORT_BLOCKS][17] */) {
+    __shared__ unsigned int s_h[17];
+    if (threadIdx.x < 17) s_h[threadIdx.x] = 0;
+    __syncthreads();
+    const uint32_t n_miss = p.ctr->n_miss;
+    const uint32_t chunk = (n_miss + gridDim.x - 1) / gridDim.x;
+    const uint32_t lo = blockIdx.x * chunk, hi = min(n_miss, lo + chunk);
+    for (uint32_t qi = lo + threadIdx.x; qi < hi; qi += 256) atomicAdd(&s_h[p.mq.len[qi]], 1u);
+    __syncthreads();
+    if (threadIdx.x < 17) block_hist[blockIdx.x * 17 + threadIdx.x] = s_h[threadIdx.x];
+}
+
+// bucket bases: warp l turns column l of block_hist into exclusive offsets (bucket-major, then block order)
+__global__ void __launch_bounds__(17 * 32) miss_base_kernel(unsigned int *block_hist, int n_blocks) {
+    __shared__ unsigned int s_tot[17];
+    const int l = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    unsigned int run = 0;
+    for (int b0 = 0; b0 < n_blocks; b0 += 32) {
+        const int b = b0 + lane;
+        const unsigned int c = b < n_blocks ? block_hist[b * 17 + l] : 0u;
+        unsigned int inc = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { unsigned int y = __shfl_up_sync(0xFFFFFFFFu, inc, o); if (lane >= o) inc += y; }
+        if (b < n_blocks) block_hist[b * 17 + l] = run + inc - c;
+        run += __shfl_sync(0xFFFFFFFFu, inc, 31);
+    }
+    if (lane == 0) s_tot[l] = run;
+    __syncthreads();
+    unsigned int base = 0;
+    for (int k = 0; k < l; k++) base += s_tot[k];
+    for (int b = lane; b < n_blocks; b += 32) block_hist[b * 17 + l] += base;
+}
+
+__global__ void __launch_bounds__(256) miss_scatter_kernel(TileParams p, const unsigned int *block_base) {
+    __shared__ unsigned int s_b[17];
+    if (threadIdx.x < 17) s_b[threadIdx.x] = block_base[blockIdx.x * 17 + threadIdx.x];
+    __syncthreads();
+    const uint32_t n_miss = p.ctr->n_miss;
+    const uint32_t chunk = (n_miss + gridDim.x - 1) / gridDim.x;
+    const uint32_t lo = blockIdx.x * chunk, hi = min(n_miss, lo + chunk);
+    for (uint32_t qi = lo + threadIdx.x; qi < hi; qi += 256) p.mq.order[atomicAdd(&s_b[p.mq.len[qi]], 1u)] = qi;
+}
+
 __global__ void __launch_bounds__(MISS_WARPS * 32) miss_kernel(TileParams p, DevTables T) {
     __shared__ MissSmem smem[MISS_WARPS];
     MissSmem &S = smem[threadIdx.x >> 5];
@@ -852,8 +903,8 @@ __global__ void __launch_bounds__(MISS_WARPS * 32) miss_kernel(TileParams p, Dev
     const uint32_t n_miss = p.ctr->n_miss;
     const uint32_t stride = gridDim.x * MISS_WARPS * 32;
     for (uint32_t q0 = (blockIdx.x * MISS_WARPS + (threadIdx.x >> 5)) * 32; q0 < n_miss; q0 += stride) {
-        const uint32_t qi = q0 + lane;
-        const bool have = qi < n_miss;
+        const bool have = q0 + lane < n_miss;
+        const uint32_t qi = have ? p.mq.order[q0 + lane] : 0u;
         uint32_t pos = 0; int len = 0;
         if (have) { pos = p.mq.pos[qi]; len = p.mq.len[qi]; }
         {   // 16 bytes at an arbitrary offset: five aligned words + funnel shifts (text is padded)
@@ -1129,9 +1180,9 @@ struct PinnedBuf {
 // three slots in flight (H2D of chunk c+1, kernels of chunk c, D2H of chunk c-1).
 struct Slot {
     DevBuf<uint8_t> w_text; DevBuf<unsigned long long> w_docoff, w_tokoff, w_sub_base;
-    DevBuf<uint32_t> w_ptok, w_mres, w_mq_pos, w_mq_roff, w_sub_count; DevBuf<uint8_t> w_mq_len, w_mq_cnt;
+    DevBuf<uint32_t> w_ptok, w_mres, w_mq_pos, w_mq_roff, w_mq_order, w_sub_count; DevBuf<uint8_t> w_mq_len, w_mq_cnt;
     DevBuf<uint32_t> w_dbits, w_pbits, w_psum, w_sfd, w_lidx, w_out, w_ltok;
-    DevBuf<unsigned long long> w_lq_start, w_lq_off; DevBuf<unsigned int> w_lq_len, w_lq_ntok, w_lq_giant, w_big_n; DevBuf<unsigned long long> w_big_dst, w_big_src, w_scan_part;
+    DevBuf<unsigned long long> w_lq_start, w_lq_off; DevBuf<unsigned int> w_lq_len, w_lq_ntok, w_lq_giant, w_big_n, w_sort_hist; DevBuf<unsigned long long> w_big_dst, w_big_src, w_scan_part;
     DevBuf<uint32_t> w_idA, w_rkA, w_idB, w_rkB, w_aux1, w_aux2; DevBuf<uint8_t> w_flag;
     Counters *d_ctr = nullptr; Counters *h_ctr = nullptr;   // h_ctr pinned
     cudaStream_t stream = nullptr;
@@ -1150,10 +1201,10 @@ struct Slot {
     }
     void destroy() {
         w_text.release(); w_docoff.release(); w_tokoff.release(); w_sub_base.release();
-        w_ptok.release(); w_mres.release(); w_mq_pos.release(); w_mq_roff.release(); w_sub_count.release();
+        w_ptok.release(); w_mres.release(); w_mq_pos.release(); w_mq_roff.release(); w_mq_order.release(); w_sub_count.release();
         w_mq_len.release(); w_mq_cnt.release();
         w_dbits.release(); w_pbits.release(); w_psum.release(); w_sfd.release(); w_lidx.release(); w_out.release(); w_ltok.release();
-        w_lq_start.release(); w_lq_off.release(); w_lq_len.release(); w_lq_ntok.release(); w_lq_giant.release(); w_big_n.release(); w_big_dst.release(); w_big_src.release(); w_scan_part.release();
+        w_lq_start.release(); w_lq_off.release(); w_lq_len.release(); w_lq_ntok.release(); w_lq_giant.release(); w_big_n.release(); w_sort_hist.release(); w_big_dst.release(); w_big_src.release(); w_scan_part.release();
         w_idA.release(); w_rkA.release(); w_idB.release(); w_rkB.release(); w_aux1.release(); w_aux2.release();
         w_flag.release();
         if (d_ctr) cudaFree(d_ctr);
@@ -1328,9 +1379,10 @@ static int run_pipeline(b200bpe *h, Slot &S, const uint8_t *d_text, uint64_t n_b
     CUDA_TRY(S.w_ptok.ensure((size_t)n_tiles * SUB_BYTES + 64));
     {   // a miss has >= 2 bytes; its tokens never outnumber its bytes
         const size_t mcap = (size_t)(n_bytes / 2) + 64;
-        CUDA_TRY(S.w_mq_pos.ensure(mcap)); CUDA_TRY(S.w_mq_roff.ensure(mcap));
+        CUDA_TRY(S.w_mq_pos.ensure(mcap)); CUDA_TRY(S.w_mq_roff.ensure(mcap)); CUDA_TRY(S.w_mq_order.ensure(mcap));
         CUDA_TRY(S.w_mq_len.ensure(mcap)); CUDA_TRY(S.w_mq_cnt.ensure(mcap));
         CUDA_TRY(S.w_mres.ensure((size_t)n_bytes + 64));
+        CUDA_TRY(S.w_sort_hist.ensure((size_t)SORT_BLOCKS * 17 + 32));
     }
     CUDA_TRY(S.w_lidx.ensure((size_t)(n_bytes >> 4) + 4));
     const size_t qcap = (size_t)(n_bytes / (SHORT_MAX + 1)) + 4;
@@ -1400,11 +1452,14 @@ static int run_pipeline(b200bpe *h, Slot &S, const uint8_t *d_text, uint64_t n_b
         p.pbits = S.w_pbits.p; p.dbits = S.w_dbits.p; p.span_first_doc = S.w_sfd.p;
         p.doc_off = d_doc_off; p.n_docs = n_docs; p.q = q; p.lidx = S.w_lidx.p; p.ltok = S.w_ltok.p;
         p.ptok = S.w_ptok.p; p.mres = S.w_mres.p;
-        p.mq = MissQ{S.w_mq_pos.p, S.w_mq_roff.p, S.w_mq_len.p, S.w_mq_cnt.p};
+        p.mq = MissQ{S.w_mq_pos.p, S.w_mq_roff.p, S.w_mq_len.p, S.w_mq_cnt.p, S.w_mq_order.p};
         p.sub_count = S.w_sub_count.p; p.sub_base = S.w_sub_base.p;
         p.out = d_out; p.tok_off = d_tok_off; p.ctr = S.d_ctr;
         p.big_dst = S.w_big_dst.p; p.big_src = S.w_big_src.p; p.big_n = S.w_big_n.p;
         probe_kernel<<<(unsigned)((n_tiles + ENC_WARPS - 1) / ENC_WARPS), ENC_WARPS * 32, 0, st>>>(p, h->T);
+        miss_hist_kernel<<<SORT_BLOCKS, 256, 0, st>>>(p, S.w_sort_hist.p);
+        miss_base_kernel<<<1, 17 * 32, 0, st>>>(S.w_sort_hist.p, SORT_BLOCKS);
+        miss_scatter_kernel<<<SORT_BLOCKS, 256, 0, st>>>(p, S.w_sort_hist.p);
         miss_kernel<<<148 * 8, MISS_WARPS * 32, 0, st>>>(p, h->T);
         CUDA_TRY(cudaEventRecord(S.ev[7], st));
         {
@@ -1415,7 +1470,7 @@ static int run_pipeline(b200bpe *h, Slot &S, const uint8_t *d_text, uint64_t n_b
         }
         gather_kernel<<<(unsigned)((n_tiles + 7) / 8), 256, 0, st>>>(p);
         big_copy_kernel<<<148 * 2, 256, 0, st>>>(p);
-        launches += 7;
+        launches += 10;
     }
     CUDA_TRY(cudaEventRecord(S.ev[4], st));
     CUDA_TRY(cudaMemcpyAsync(S.h_ctr, S.d_ctr, sizeof(Counters), cudaMemcpyDeviceToHost, st));

@@ -156,10 +156,20 @@ B2_HD uint32_t span_boundaries(const TextAccess &t, int64_t w, SpanStats *stats 
         slow |= L & ((pX & pHi) | pAPOS | (pL & aposNear));
         // digits: groups of three from the run start
         b |= m.N & ~pN;
-        {
-            const uint64_t a1 = m.NA << 1, a2 = m.NA << 2, n2 = m.N << 2, n3 = m.N << 3;
-            const uint64_t k1 = a1 & ~n2, k2 = a1 & a2 & ~n3;
-            slow |= m.N & pN & ~(k1 | k2);
+        {   // `\p{N}{1,3}`: a digit starts a piece iff the count of digits before it in its run is a
+            // multiple of 3.  Runs of ASCII digits that start within the 8-byte look-back are counted with
+            // shifts; longer or non-ASCII runs go the slow way.
+            const uint64_t A = m.NA;
+            const uint64_t rs = A & ~(m.N << 1);                       // an ASCII digit that starts its run
+            const uint64_t c1 = A << 1, c2 = c1 & (A << 2), c3 = c2 & (A << 3), c4 = c3 & (A << 4);
+            const uint64_t c5 = c4 & (A << 5), c6 = c5 & (A << 6), c7 = c6 & (A << 7);
+            const uint64_t k1 = rs << 1, k2 = c1 & (rs << 2), k3 = c2 & (rs << 3), k4 = c3 & (rs << 4);
+            const uint64_t k5 = c4 & (rs << 5), k6 = c5 & (rs << 6), k7 = c6 & (rs << 7);
+            const uint64_t known = (k1 | k2 | k3 | k4 | k5 | k6 | k7) & ~(m.D | (m.D << 1) | (m.D << 2) | (m.D << 3) |
+                                   (m.D << 4) | (m.D << 5) | (m.D << 6));
+            (void)c7;
+            b |= A & pN & known & (k3 | k6);
+            slow |= m.N & pN & ~(A & known);
         }
         b |= X & ~(pX | pSP);
         b |= m.NL & (pL | pN);
@@ -178,10 +188,20 @@ B2_HD uint32_t span_boundaries(const TextAccess &t, int64_t w, SpanStats *stats 
         b |= m.O & (pL | pN | ((m.WS | m.NL) << 1));
         slow |= m.O & (pM | (m.SLASH << 1));
         b |= m.N & ~pN;
-        {
-            const uint64_t a1 = m.NA << 1, a2 = m.NA << 2, n2 = m.N << 2, n3 = m.N << 3;
-            const uint64_t k1 = a1 & ~n2, k2 = a1 & a2 & ~n3;
-            slow |= m.N & pN & ~(k1 | k2);
+        {   // `\p{N}{1,3}`: a digit starts a piece iff the count of digits before it in its run is a
+            // multiple of 3.  Runs of ASCII digits that start within the 8-byte look-back are counted with
+            // shifts; longer or non-ASCII runs go the slow way.
+            const uint64_t A = m.NA;
+            const uint64_t rs = A & ~(m.N << 1);                       // an ASCII digit that starts its run
+            const uint64_t c1 = A << 1, c2 = c1 & (A << 2), c3 = c2 & (A << 3), c4 = c3 & (A << 4);
+            const uint64_t c5 = c4 & (A << 5), c6 = c5 & (A << 6), c7 = c6 & (A << 7);
+            const uint64_t k1 = rs << 1, k2 = c1 & (rs << 2), k3 = c2 & (rs << 3), k4 = c3 & (rs << 4);
+            const uint64_t k5 = c4 & (rs << 5), k6 = c5 & (rs << 6), k7 = c6 & (rs << 7);
+            const uint64_t known = (k1 | k2 | k3 | k4 | k5 | k6 | k7) & ~(m.D | (m.D << 1) | (m.D << 2) | (m.D << 3) |
+                                   (m.D << 4) | (m.D << 5) | (m.D << 6));
+            (void)c7;
+            b |= A & pN & known & (k3 | k6);
+            slow |= m.N & pN & ~(A & known);
         }
         b |= m.NL & (pL | pN);
         slow |= m.NL & pM;
