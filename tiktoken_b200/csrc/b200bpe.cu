@@ -1460,7 +1460,7 @@ static int run_pipeline(b200bpe *h, Slot &S, const uint8_t *d_text, uint64_t n_b
         miss_hist_kernel<<<SORT_BLOCKS, 256, 0, st>>>(p, S.w_sort_hist.p);
         miss_base_kernel<<<1, 17 * 32, 0, st>>>(S.w_sort_hist.p, SORT_BLOCKS);
         miss_scatter_kernel<<<SORT_BLOCKS, 256, 0, st>>>(p, S.w_sort_hist.p);
-        miss_kernel<<<148 * 8, MISS_WARPS * 32, 0, st>>>(p, h->T);
+        miss_kernel<<<148 * 16, MISS_WARPS * 32, 0, st>>>(p, h->T);
         CUDA_TRY(cudaEventRecord(S.ev[7], st));
         {
             const long long nb = (n_tiles + SCAN_ITEMS - 1) / SCAN_ITEMS;

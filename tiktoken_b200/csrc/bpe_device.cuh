@@ -32,8 +32,8 @@ struct U4 { uint32_t x, y, z, w; };                // host mirror of uint4
 struct DevTables {
     const uint32_t *byte_id;      // [256]
     const uint32_t *pair2;        // [65536] rank of the 2-byte token b0,b1 (index b0*256+b1) or RANK_MAX
-    const U4 *pair_tab;           // slots {a, b, rank, 0}; empty: a == 0xFFFFFFFF
-    uint32_t pair_mask;
+    const U4 *pair_tab;           // buckets of two slots {a, b, rank, 0}; empty slot: a == 0xFFFFFFFF
+    uint32_t pair_mask;           // number of buckets - 1
     const U4 *piece_tab;          // 2 x U4 per slot: {k0lo,k0hi,k1lo,k1hi} {len, rank, 0, 0}; empty: len == 0
     uint32_t piece_mask;
     const U4 *long_tab;           // 2 x U4 per slot: {hlo, hhi, blob_off, len} {rank,0,0,0}; empty: len == 0
@@ -77,12 +77,15 @@ B2_HD uint64_t long_hash_step(uint64_t h, uint64_t w) {
 }
 B2_HD uint64_t long_hash_init(uint64_t len) { return len * 0xC2B2AE3D27D4EB4Full + 0x165667B19E3779F9ull; }
 
+// The pair table is probed in BUCKETS of two 16-byte slots (one 32-byte sector): both slots of a
+// bucket are loaded together, a bucket with a free slot ends the chain.  pair_mask = n_buckets - 1.
 B2_HD uint32_t pair_lookup(const DevTables &T, uint32_t a, uint32_t b) {
     uint32_t s = pair_hash(a, b) & T.pair_mask;
     for (;;) {
-        U4 e = B2_LDG_U4(T.pair_tab + s);
-        if (e.x == a && e.y == b) return e.z;
-        if (e.x == 0xFFFFFFFFu) return RANK_MAX;
+        const U4 e0 = B2_LDG_U4(T.pair_tab + 2 * s), e1 = B2_LDG_U4(T.pair_tab + 2 * s + 1);
+        if (e0.x == a && e0.y == b) return e0.z;
+        if (e1.x == a && e1.y == b) return e1.z;
+        if (e1.x == 0xFFFFFFFFu) return RANK_MAX;          // slots fill in order: a free second slot ends the chain
         s = (s + 1) & T.pair_mask;
     }
 }
@@ -92,16 +95,19 @@ B2_HD uint32_t pair_lookup(const DevTables &T, uint32_t a, uint32_t b) {
 B2_HD void pair_lookup2(const DevTables &T, uint32_t a1, uint32_t b1, uint32_t a2, uint32_t b2, uint32_t &r1,
                         uint32_t &r2) {
     uint32_t s1 = pair_hash(a1, b1) & T.pair_mask, s2 = pair_hash(a2, b2) & T.pair_mask;
-    U4 e1 = B2_LDG_U4(T.pair_tab + s1), e2 = B2_LDG_U4(T.pair_tab + s2);
+    U4 e10 = B2_LDG_U4(T.pair_tab + 2 * s1), e11 = B2_LDG_U4(T.pair_tab + 2 * s1 + 1);
+    U4 e20 = B2_LDG_U4(T.pair_tab + 2 * s2), e21 = B2_LDG_U4(T.pair_tab + 2 * s2 + 1);
     for (;;) {
-        if (e1.x == a1 && e1.y == b1) { r1 = e1.z; break; }
-        if (e1.x == 0xFFFFFFFFu) { r1 = RANK_MAX; break; }
-        s1 = (s1 + 1) & T.pair_mask; e1 = B2_LDG_U4(T.pair_tab + s1);
+        if (e10.x == a1 && e10.y == b1) { r1 = e10.z; break; }
+        if (e11.x == a1 && e11.y == b1) { r1 = e11.z; break; }
+        if (e11.x == 0xFFFFFFFFu) { r1 = RANK_MAX; break; }
+        s1 = (s1 + 1) & T.pair_mask; e10 = B2_LDG_U4(T.pair_tab + 2 * s1); e11 = B2_LDG_U4(T.pair_tab + 2 * s1 + 1);
     }
     for (;;) {
-        if (e2.x == a2 && e2.y == b2) { r2 = e2.z; break; }
-        if (e2.x == 0xFFFFFFFFu) { r2 = RANK_MAX; break; }
-        s2 = (s2 + 1) & T.pair_mask; e2 = B2_LDG_U4(T.pair_tab + s2);
+        if (e20.x == a2 && e20.y == b2) { r2 = e20.z; break; }
+        if (e21.x == a2 && e21.y == b2) { r2 = e21.z; break; }
+        if (e21.x == 0xFFFFFFFFu) { r2 = RANK_MAX; break; }
+        s2 = (s2 + 1) & T.pair_mask; e20 = B2_LDG_U4(T.pair_tab + 2 * s2); e21 = B2_LDG_U4(T.pair_tab + 2 * s2 + 1);
     }
 }
 
@@ -251,16 +257,19 @@ B2_HD uint32_t merge_short_conv(const DevTables &T, ByteFn byte_at, int n, int n
         uint32_t r1 = RANK_MAX, r2 = RANK_MAX;
         bool p1 = need_r, p2 = need_l;
         while (B2_ANY(group, p1 || p2)) {
+            U4 e0 = {0, 0, 0, 0}, e1 = {0, 0, 0, 0}, f0 = {0, 0, 0, 0}, f1 = {0, 0, 0, 0};
+            if (p1) { e0 = B2_LDG_U4(T.pair_tab + 2 * s1); e1 = B2_LDG_U4(T.pair_tab + 2 * s1 + 1); }
+            if (p2) { f0 = B2_LDG_U4(T.pair_tab + 2 * s2); f1 = B2_LDG_U4(T.pair_tab + 2 * s2 + 1); }
             if (p1) {
-                const U4 e = B2_LDG_U4(T.pair_tab + s1);
-                if (e.x == a1 && e.y == b1) { r1 = e.z; p1 = false; }
-                else if (e.x == 0xFFFFFFFFu) p1 = false;
+                if (e0.x == a1 && e0.y == b1) { r1 = e0.z; p1 = false; }
+                else if (e1.x == a1 && e1.y == b1) { r1 = e1.z; p1 = false; }
+                else if (e1.x == 0xFFFFFFFFu) p1 = false;
                 else s1 = (s1 + 1) & T.pair_mask;
             }
             if (p2) {
-                const U4 e = B2_LDG_U4(T.pair_tab + s2);
-                if (e.x == a2 && e.y == b2) { r2 = e.z; p2 = false; }
-                else if (e.x == 0xFFFFFFFFu) p2 = false;
+                if (f0.x == a2 && f0.y == b2) { r2 = f0.z; p2 = false; }
+                else if (f1.x == a2 && f1.y == b2) { r2 = f1.z; p2 = false; }
+                else if (f1.x == 0xFFFFFFFFu) p2 = false;
                 else s2 = (s2 + 1) & T.pair_mask;
             }
         }

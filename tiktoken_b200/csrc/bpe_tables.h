@@ -99,13 +99,17 @@ inline int build_tables(const uint8_t *tok_bytes, const uint64_t *tok_off, const
         }
     }
     H.n_pairs = pairs.size();
-    uint32_t pc = pow2_at_least((uint64_t)pairs.size() * 3 + 2);      // load factor <= 1/3
-    H.pair_mask = pc - 1;
-    H.pair_tab.assign(pc, U4{0xFFFFFFFFu, 0xFFFFFFFFu, RANK_MAX, 0});
+    // buckets of two slots; capacity >= 3x the entries
+    uint32_t nbuckets = pow2_at_least(((uint64_t)pairs.size() * 3 + 2) / 2 + 1);
+    H.pair_mask = nbuckets - 1;
+    H.pair_tab.assign((size_t)nbuckets * 2, U4{0xFFFFFFFFu, 0xFFFFFFFFu, RANK_MAX, 0});
     for (auto &p : pairs) {
         uint32_t s = pair_hash(p.a, p.b) & H.pair_mask;
-        while (H.pair_tab[s].x != 0xFFFFFFFFu) s = (s + 1) & H.pair_mask;
-        H.pair_tab[s] = U4{p.a, p.b, p.r, 0};
+        for (;;) {
+            if (H.pair_tab[2 * s].x == 0xFFFFFFFFu) { H.pair_tab[2 * s] = U4{p.a, p.b, p.r, 0}; break; }
+            if (H.pair_tab[2 * s + 1].x == 0xFFFFFFFFu) { H.pair_tab[2 * s + 1] = U4{p.a, p.b, p.r, 0}; break; }
+            s = (s + 1) & H.pair_mask;
+        }
     }
     uint32_t sc = pow2_at_least((uint64_t)n_short * 3 + 2);
     H.piece_mask = sc - 1;
