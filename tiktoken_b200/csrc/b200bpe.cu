@@ -69,11 +69,12 @@ struct Counters {            // device-resident, zeroed per call
 };
 
 static const uint32_t GIANT_MIN = 4096;      // pieces longer than this get a whole block (kernel 3b)
+static const uint32_t LONG_SCRATCH_MIN = 256; // pieces longer than this merge in global scratch (= MID_MAX)
 
 struct LongQ {               // queue of pieces longer than SHORT_MAX bytes
     unsigned long long *start;   // byte offset of the piece
     unsigned int *len;
-    unsigned long long *off;     // offset of its region in the long scratch / ltok
+    unsigned long long *off;     // offset of its region in the global merge scratch (pieces > LONG_SCRATCH_MIN only)
     unsigned int *ntok;
     unsigned int *giant;         // indices (into this queue) of the pieces longer than GIANT_MIN
 };
@@ -169,8 +170,15 @@ __global__ void __launch_bounds__(256) find_long_kernel(const uint32_t *__restri
         }
         const long long len = nxt - s;
         if (len > SHORT_MAX) {
-            unsigned int i = atomicAdd(&ctr->n_long, 1u);
-            unsigned long long off = atomicAdd(&ctr->long_bytes, (unsigned long long)len);
+            // one queue-slot atomic per warp iteration (the lanes that found a long piece together)
+            const uint32_t peers = __activemask();
+            unsigned int i = 0;
+            if ((threadIdx.x & 31) == __ffs(peers) - 1) i = atomicAdd(&ctr->n_long, (unsigned int)__popc(peers));
+            i = __shfl_sync(peers, i, __ffs(peers) - 1) + __popc(peers & ((1u << (threadIdx.x & 31)) - 1u));
+            // tokens land in ltok at the piece's own byte offset (tokens <= bytes, pieces are disjoint);
+            // only pieces beyond the shared-memory path need a region of the global merge scratch
+            unsigned long long off = 0;
+            if (len > LONG_SCRATCH_MIN) off = atomicAdd(&ctr->long_bytes, (unsigned long long)len);
             q.start[i] = (unsigned long long)s; q.len[i] = (unsigned int)len; q.off[i] = off;
             lidx[s >> 4] = i;
             if (len > GIANT_MIN) q.giant[atomicAdd(&ctr->n_giant, 1u)] = i;
@@ -220,7 +228,7 @@ __device__ uint32_t long_piece_warp(const DevTables &T, const uint8_t *__restric
                 for (uint32_t i = 0; i < n; i += 8) {
                     uint64_t w = 0;
                     for (uint32_t k = 0; k < 8 && i + k < n; k++) w |= (uint64_t)piece[i + k] << (8 * k);
-                    h = long_hash_step(h, w);
+                    h = long_hash_step(h, w, i / 8);
                 }
                 r = piece_lookup_long(T, h, n, [&](uint32_t i) { return piece[i]; });
             }
@@ -360,16 +368,15 @@ __device__ uint32_t mid_piece_warp(const DevTables &T, const uint8_t *__restrict
     const uint32_t FULL = 0xFFFFFFFFu;
     // whole-piece probe (src/lib.rs:367-368); only a token of exactly this length can match
     if (n <= T.max_token_len && T.n_long_tokens) {
-        uint32_t r = RANK_MAX;
-        if (lane == 0) {
-            uint64_t h = long_hash_init(n);
-            for (uint32_t i = 0; i < n; i += 8) {
-                uint64_t w = 0;
-                for (uint32_t k = 0; k < 8 && i + k < n; k++) w |= (uint64_t)piece[i + k] << (8 * k);
-                h = long_hash_step(h, w);
-            }
-            r = piece_lookup_long(T, h, n, [&](uint32_t i) { return piece[i]; });
+        uint64_t hw = 0;                                     // one 8-byte word per lane (n <= 256)
+        if ((uint32_t)lane * 8u < n) {
+            uint64_t w = 0;
+            for (uint32_t k = 0; k < 8 && (uint32_t)lane * 8u + k < n; k++) w |= (uint64_t)piece[lane * 8 + k] << (8 * k);
+            hw = long_hash_word(w, (uint32_t)lane);
         }
+        const uint32_t hlo = __reduce_xor_sync(FULL, (uint32_t)hw), hhi = __reduce_xor_sync(FULL, (uint32_t)(hw >> 32));
+        uint32_t r = RANK_MAX;
+        if (lane == 0) r = piece_lookup_long(T, long_hash_init(n) ^ (((uint64_t)hhi << 32) | hlo), n, [&](uint32_t i) { return piece[i]; });
         r = __shfl_sync(FULL, r, 0);
         if (r != RANK_MAX) { if (lane == 0) out[0] = r; return 1; }
     }
@@ -436,30 +443,148 @@ __device__ uint32_t mid_piece_warp(const DevTables &T, const uint8_t *__restrict
     return cnt;
 }
 
+// Two pieces per warp for the bulk of the mid-size class (17..128 bytes): each HALF-warp owns one
+// piece (part p = slot*16 + lane_in_half, <= 8 slots) and both halves walk the same instruction
+// stream, so an instruction serves two merges.  Same algorithm and data layout as mid_piece_warp;
+// the group primitives (redux.sync / shfl) simply run on the half-warp masks.
+static const uint32_t PAIR_MAX = 128;
+
+__device__ void mid_piece_pair(const DevTables &T, const uint8_t *__restrict__ piece, uint32_t n /* 0 = idle half */,
+                               MidSmem &M, uint32_t *__restrict__ out, uint32_t *ntok_out, uint32_t *err) {
+    const int lane = threadIdx.x & 31, half = lane >> 4, hl = lane & 15;
+    const uint32_t gmask = half ? 0xFFFF0000u : 0x0000FFFFu;
+    const int lead = half * 16;
+    uint32_t *id = M.id + half * PAIR_MAX, *rk = M.rk + half * PAIR_MAX;       // MidSmem holds 256 parts: 128 per half
+    uint32_t *am = M.am + half * 4;                                          // 8 x 16-bit alive words per half
+    uint16_t *am16 = reinterpret_cast<uint16_t *>(am);
+    bool active = n != 0;
+    // whole-piece probe by the first lane of each half
+    if (active && n <= T.max_token_len && T.n_long_tokens) {
+        uint64_t hw = 0;                                     // one 8-byte word per lane of the half (n <= 128)
+        if ((uint32_t)hl * 8u < n) {
+            uint64_t w = 0;
+            for (uint32_t k = 0; k < 8 && (uint32_t)hl * 8u + k < n; k++) w |= (uint64_t)piece[hl * 8 + k] << (8 * k);
+            hw = long_hash_word(w, (uint32_t)hl);
+        }
+        const uint32_t hlo = __reduce_xor_sync(gmask, (uint32_t)hw), hhi = __reduce_xor_sync(gmask, (uint32_t)(hw >> 32));
+        uint32_t r = RANK_MAX;
+        if (hl == 0) r = piece_lookup_long(T, long_hash_init(n) ^ (((uint64_t)hhi << 32) | hlo), n, [&](uint32_t i) { return piece[i]; });
+        r = __shfl_sync(gmask, r, lead);
+        if (r != RANK_MAX) { if (hl == 0) { out[0] = r; *ntok_out = 1; } active = false; n = 0; }
+    }
+    const int n_slots = (int)((n + 15) >> 4);
+    for (int s = 0; s < 8; s++) {
+        const uint32_t p = (uint32_t)s * 16u + (uint32_t)hl;
+        uint32_t i0 = 0, r0 = RANK_MAX;
+        if (p < n) {
+            const uint32_t b = piece[p];
+            i0 = __ldg(T.byte_id + b);
+            if (p + 1 < n) r0 = __ldg(T.pair2 + ((b << 8) | piece[p + 1]));
+        }
+        id[p] = i0; rk[p] = r0;
+        const uint32_t al = __ballot_sync(0xFFFFFFFFu, p < n);
+        if (hl == 0) am16[s] = (uint16_t)(al >> lead);
+    }
+    __syncwarp();
+    auto next_al = [&](int p) -> int {                        // next alive part after p (same value in all lanes of the half)
+        const int w0 = p >> 4, b = p & 15;
+        uint32_t m = (uint32_t)am16[w0] & ~((2u << b) - 1u) & 0xFFFFu;
+        if (m) return w0 * 16 + __ffs(m) - 1;
+        for (int w = w0 + 1; w < 8; w++) { m = am16[w]; if (m) return w * 16 + __ffs(m) - 1; }
+        return -1;
+    };
+    auto prev_al = [&](int p) -> int {
+        const int w0 = p >> 4, b = p & 15;
+        uint32_t m = (uint32_t)am16[w0] & ((1u << b) - 1u);
+        if (m) return w0 * 16 + 31 - __clz((int)m);
+        for (int w = w0 - 1; w >= 0; w--) { m = am16[w]; if (m) return w * 16 + 31 - __clz((int)m); }
+        return -1;
+    };
+    while (__any_sync(0xFFFFFFFFu, active)) {
+        uint32_t best = RANK_MAX, bp = 0xFFFFu;
+        for (int s = 0; s < n_slots; s++) {
+            const uint32_t r = rk[s * 16 + hl];
+            if (r < best) { best = r; bp = (uint32_t)s * 16u + (uint32_t)hl; }
+        }
+        const uint32_t g = __reduce_min_sync(gmask, best);
+        const int bj = (int)__reduce_min_sync(gmask, best == g ? bp : 0xFFFFFFFFu);   // leftmost on ties
+        if (g == RANK_MAX) active = false;
+        int j2 = -1, j3 = -1, jp = -1;
+        if (active) { j2 = next_al(bj); j3 = next_al(j2); jp = prev_al(bj); }
+        uint32_t r = RANK_MAX;
+        {   // lane 0 of the half probes (merged, right neighbour), lane 1 (left neighbour, merged)
+            const int jn = hl == 0 ? j3 : jp;
+            if (active && hl < 2 && jn >= 0) {
+                const uint32_t o = id[jn];
+                r = pair_lookup(T, hl == 0 ? g : o, hl == 0 ? o : g);
+            }
+        }
+        const uint32_t rr = __shfl_sync(gmask, r, lead), rl = __shfl_sync(gmask, r, lead + 1);
+        if (active && hl == 0) {
+            id[bj] = g; rk[bj] = (j3 >= 0) ? rr : RANK_MAX; rk[j2] = RANK_MAX;
+            if (jp >= 0) rk[jp] = rl;
+            am16[j2 >> 4] &= (uint16_t)~(1u << (j2 & 15));
+        }
+        __syncwarp();
+    }
+    if (n) {
+        uint32_t cnt = 0; bool bad = false;
+        for (int s = 0; s < n_slots; s++) {
+            const uint32_t m = am16[s];
+            if ((m >> hl) & 1u) {
+                const uint32_t x = id[s * 16 + hl];
+                out[cnt + __popc(m & ((1u << hl) - 1u))] = x;
+                bad |= x >= PSEUDO_BASE;
+            }
+            cnt += __popc(m);
+        }
+        if (bad) atomicOr(err, ERR_NOBYTE);
+        if (hl == 0) *ntok_out = cnt;
+    }
+    __syncwarp();
+}
+
 static const int LONG_WARPS = 8;               // warps per block of long_piece_kernel
 
 __global__ void __launch_bounds__(LONG_WARPS * 32) long_piece_kernel(const uint8_t *__restrict__ text, DevTables T, LongQ q,
                                                                     LongScratch S, uint32_t *ltok, Counters *ctr) {
     __shared__ MidSmem s_mid[LONG_WARPS];
-    const int lane = threadIdx.x & 31;
+    const int lane = threadIdx.x & 31, half = lane >> 4;
     const unsigned int n_long = ctr->n_long;
     for (;;) {
-        unsigned int i = 0;
-        if (lane == 0) i = atomicAdd(&ctr->long_head, 1u);
-        i = __shfl_sync(0xFFFFFFFFu, i, 0);
-        if (i >= n_long) break;
-        const uint32_t len = q.len[i];
-        if (len > GIANT_MIN) continue;                          // handled by giant_piece_kernel (whole block)
-        const unsigned long long off = q.off[i];
-        uint32_t nt;
-        if (len <= MID_MAX) nt = mid_piece_warp(T, text + q.start[i], len, s_mid[threadIdx.x >> 5], ltok + off, &ctr->err);
-        else {
-            LongScratch P = S;
-            P.idA += off; P.rkA += off; P.idB += off; P.rkB += off; P.aux1 += off; P.aux2 += off; P.flag += off;
-            nt = long_piece_warp(T, text + q.start[i], len, P, ltok + off, &ctr->err);
+        unsigned int i0 = 0;
+        if (lane == 0) i0 = atomicAdd(&ctr->long_head, 2u);
+        i0 = __shfl_sync(0xFFFFFFFFu, i0, 0);
+        if (i0 >= n_long) break;
+        const unsigned int i1 = i0 + 1;
+        const uint32_t len0 = q.len[i0], len1 = i1 < n_long ? q.len[i1] : 0u;
+        MidSmem &M = s_mid[threadIdx.x >> 5];
+        // two pieces of <= 128 bytes: one per half-warp, in lockstep
+        const bool pair0 = len0 <= PAIR_MAX, pair1 = len1 != 0 && len1 <= PAIR_MAX;
+        if (pair0 || pair1) {
+            const unsigned int mi = half ? i1 : i0;
+            const bool mine = half ? pair1 : pair0;
+            const unsigned long long st0 = mine ? q.start[mi] : 0ull;
+            uint32_t nt = 0;
+            mid_piece_pair(T, text + st0, mine ? (half ? len1 : len0) : 0u, M, ltok + st0, &nt, &ctr->err);
+            if (mine && (lane & 15) == 0) q.ntok[mi] = nt;
+            __syncwarp();
         }
-        if (lane == 0) q.ntok[i] = nt;
-        __syncwarp();
+        for (int k = 0; k < 2; k++) {                           // the rest: whole warp, one after the other
+            const unsigned int i = k ? i1 : i0;
+            const uint32_t len = k ? len1 : len0;
+            if (len == 0 || len <= PAIR_MAX || len > GIANT_MIN) continue;   // giant pieces: giant_piece_kernel
+            const unsigned long long off = q.off[i], st0 = q.start[i];
+            uint32_t nt;
+            if (len <= MID_MAX) nt = mid_piece_warp(T, text + st0, len, M, ltok + st0, &ctr->err);
+            else {
+                LongScratch P = S;
+                P.idA += off; P.rkA += off; P.idB += off; P.rkB += off; P.aux1 += off; P.aux2 += off; P.flag += off;
+                nt = long_piece_warp(T, text + st0, len, P, ltok + st0, &ctr->err);
+            }
+            if (lane == 0) q.ntok[i] = nt;
+            __syncwarp();
+        }
     }
 }
 
@@ -493,7 +618,7 @@ __device__ uint32_t long_piece_block(const DevTables &T, const uint8_t *__restri
             for (uint32_t i = 0; i < n; i += 8) {
                 uint64_t w = 0;
                 for (uint32_t k = 0; k < 8 && i + k < n; k++) w |= (uint64_t)piece[i + k] << (8 * k);
-                h = long_hash_step(h, w);
+                h = long_hash_step(h, w, i / 8);
             }
             r = piece_lookup_long(T, h, n, [&](uint32_t i) { return piece[i]; });
             s_red[0] = r;
@@ -623,7 +748,7 @@ __global__ void __launch_bounds__(GIANT_THREADS) giant_piece_kernel(const uint8_
         const unsigned long long off = q.off[i];
         LongScratch P = S;
         P.idA += off; P.rkA += off; P.idB += off; P.rkB += off; P.aux1 += off; P.aux2 += off; P.flag += off;
-        const uint32_t nt = long_piece_block(T, text + q.start[i], q.len[i], P, ltok + off, &ctr->err);
+        const uint32_t nt = long_piece_block(T, text + q.start[i], q.len[i], P, ltok + q.start[i], &ctr->err);
         if (threadIdx.x == 0) q.ntok[i] = nt;
     }
 }
@@ -1070,7 +1195,7 @@ __global__ void __launch_bounds__(256) gather_kernel(TileParams p) {
             } else {
                 const uint32_t qi = v & PT_PAYLOAD;
                 const uint32_t nt = p.q.ntok[qi];
-                const unsigned long long lsrc = p.q.off[qi];
+                const unsigned long long lsrc = p.q.start[qi];
                 if (nt <= 32) { for (uint32_t x = 0; x < nt; x++) p.out[k + x] = p.ltok[lsrc + x]; }
                 else { big_dst = k; big_src = lsrc; big_n = nt; }   // > 32 tokens => > 32 bytes: at most one per span
                 k += nt;
@@ -1434,7 +1559,7 @@ static int run_pipeline(b200bpe *h, Slot &S, const uint8_t *d_text, uint64_t n_b
         long_blocks = (S.h_ctr->n_long + LONG_WARPS - 1) / LONG_WARPS;
         if (long_blocks > 148 * 8) long_blocks = 148 * 8;
     }
-    CUDA_TRY(S.w_ltok.ensure(long_cap));
+    CUDA_TRY(S.w_ltok.ensure((size_t)n_bytes + 4));
     if (long_blocks) {
         CUDA_TRY(S.w_idA.ensure(long_cap)); CUDA_TRY(S.w_rkA.ensure(long_cap));
         CUDA_TRY(S.w_idB.ensure(long_cap)); CUDA_TRY(S.w_rkB.ensure(long_cap));

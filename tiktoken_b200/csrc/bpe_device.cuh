@@ -70,11 +70,15 @@ B2_HD uint64_t piece_hash(uint64_t k0, uint64_t k1, uint32_t len) {
     return h;
 }
 
-// 64-bit hash of a byte string given as little-endian u64 words (last one zero padded)
-B2_HD uint64_t long_hash_step(uint64_t h, uint64_t w) {
-    h = (h ^ w) * 0x9E3779B97F4A7C15ull;
-    return h ^ (h >> 32);
+// 64-bit hash of a byte string given as little-endian u64 words (last one zero padded):
+// init(len) XOR the mixes of (word, index) -- order-independent, so a warp hashes a piece with one
+// word per lane and an XOR reduction.
+B2_HD uint64_t long_hash_word(uint64_t w, uint32_t i) {
+    uint64_t x = (w ^ ((uint64_t)(i + 1) * 0x9E3779B97F4A7C15ull)) * 0xC2B2AE3D27D4EB4Full;
+    x ^= x >> 29; x *= 0x165667B19E3779F9ull;
+    return x ^ (x >> 32);
 }
+B2_HD uint64_t long_hash_step(uint64_t h, uint64_t w, uint32_t i) { return h ^ long_hash_word(w, i); }
 B2_HD uint64_t long_hash_init(uint64_t len) { return len * 0xC2B2AE3D27D4EB4Full + 0x165667B19E3779F9ull; }
 
 // The pair table is probed in BUCKETS of two 16-byte slots (one 32-byte sector): both slots of a

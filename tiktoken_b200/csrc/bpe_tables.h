@@ -50,7 +50,7 @@ inline uint64_t long_hash_bytes(const uint8_t *p, uint32_t len) {
         uint8_t b[8] = {0};
         memcpy(b, p + i, len - i < 8 ? len - i : 8);
         uint64_t w; memcpy(&w, b, 8);
-        h = long_hash_step(h, w);
+        h = long_hash_step(h, w, i / 8);
     }
     return h;
 }
