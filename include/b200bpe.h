@@ -97,9 +97,9 @@ int b200bpe_decode_batch(b200bpe_t *h, const uint32_t *tokens, const uint64_t *t
 
 /* Per-stage device timings (ms, CUDA events on the engine stream) of the most recent encode
  * call on this handle: [0] mark documents, [1] pre-tokenise, [2] long-piece scan + merge,
- * [3] encode kernel, [4] total device time, [5] H2D, [6] D2H, [7] count scan + gather.
- * Also the kernel launch count. */
-int b200bpe_last_timings(b200bpe_t *h, float *ms8, uint32_t *n_launches);
+ * [3] encode stage (probe + miss sort + miss merge), [4] total device time, [5] H2D, [6] D2H,
+ * [7] count scan + gather, [8] probe kernel alone.  Also the kernel launch count. */
+int b200bpe_last_timings(b200bpe_t *h, float *ms9, uint32_t *n_launches);
 
 /* Sizes of the device tables (bytes) for reporting: [0] piece table, [1] pair table,
  * [2] long-token table + blob, [3] Unicode class tables. */

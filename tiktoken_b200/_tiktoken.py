@@ -247,10 +247,10 @@ class CoreBPE:
 
     # ---- measurement hooks ----------------------------------------------------------------------
     def last_timings(self) -> dict:
-        ms = (C.c_float * 8)()
+        ms = (C.c_float * 9)()
         n = C.c_uint32(0)
         self._L.b200bpe_last_timings(self._h, ms, C.byref(n))
-        keys = ["mark_docs_ms", "pretok_ms", "long_ms", "encode_ms", "device_total_ms", "h2d_ms", "d2h_ms", "gather_ms"]
+        keys = ["mark_docs_ms", "pretok_ms", "long_ms", "encode_ms", "device_total_ms", "h2d_ms", "d2h_ms", "gather_ms", "probe_ms"]
         d = {k: float(ms[i]) for i, k in enumerate(keys)}
         d["launches"] = int(n.value)
         return d

@@ -5,13 +5,16 @@
 // whole batch:
 //
 //   mark_docs_kernel      doc_off[] -> doc-start bitmask D + first-doc-per-span index
-//   pretok_kernel<PAT>    UTF-8 bytes + D -> piece-start bitmask P   (position-parallel regex rules)
-//   find_long_kernel      P -> queue of pieces longer than 16 bytes (+ scratch offsets)
-//   long_piece_kernel     one warp per long piece: whole-piece probe, then exact round-synchronous
-//                         min-rank merging in HBM/L2 scratch
-//   encode_tiles_kernel   4 KiB tiles: per-piece table probe (1 sector), per-thread merge of the
-//                         misses in shared memory, in-tile compaction, decoupled look-back for the
-//                         global token offset, token + per-document offset write-out
+//   pretok_kernel<PAT>    UTF-8 bytes + D -> piece-start bitmask P   (bit-parallel regex rules)
+//   find_long_kernel      P -> queue of pieces longer than 16 bytes
+//   long_piece_kernel     17..4096 bytes: warp / half-warp per piece, one exact merge per round in
+//   giant_piece_kernel    shared memory; > 4096 bytes: a block per piece, round-synchronous merge
+//   probe_kernel          one warp per 1 KiB sub-tile: whole-piece table probe of every short piece
+//                         (one 32 B sector each), one slot per piece, misses -> global queue
+//   miss_{hist,base,scatter}, miss_kernel   the ~5 % misses, sorted by length, one piece per lane,
+//                         warp-convergent exact min-rank merge
+//   scan_{partial,top,final}, gather_kernel, big_copy_kernel   token counts -> offsets -> tokens and
+//                         per-document offsets at their final place
 //
 // No tensor cores: nothing here is a contraction.  The work is byte/integer, bound by HBM reads
 // of the text, L2 probes of the rank tables and instruction issue.
@@ -1311,8 +1314,8 @@ struct Slot {
     DevBuf<uint32_t> w_idA, w_rkA, w_idB, w_rkB, w_aux1, w_aux2; DevBuf<uint8_t> w_flag;
     Counters *d_ctr = nullptr; Counters *h_ctr = nullptr;   // h_ctr pinned
     cudaStream_t stream = nullptr;
-    cudaEvent_t ev[8];
-    float last_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    cudaEvent_t ev[9];
+    float last_ms[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
     uint32_t last_launches = 0;
     bool ok = false;
 
@@ -1320,7 +1323,7 @@ struct Slot {
         cudaError_t e = cudaMalloc((void **)&d_ctr, sizeof(Counters));
         if (e == cudaSuccess) e = cudaHostAlloc((void **)&h_ctr, sizeof(Counters), cudaHostAllocDefault);
         if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking);
-        for (int i = 0; i < 8 && e == cudaSuccess; i++) e = cudaEventCreate(&ev[i]);
+        for (int i = 0; i < 9 && e == cudaSuccess; i++) e = cudaEventCreate(&ev[i]);
         ok = (e == cudaSuccess);
         return e;
     }
@@ -1334,7 +1337,7 @@ struct Slot {
         w_flag.release();
         if (d_ctr) cudaFree(d_ctr);
         if (h_ctr) cudaFreeHost(h_ctr);
-        if (ok) { for (int i = 0; i < 8; i++) cudaEventDestroy(ev[i]); }
+        if (ok) { for (int i = 0; i < 9; i++) cudaEventDestroy(ev[i]); }
         if (stream) cudaStreamDestroy(stream);
     }
 };
@@ -1364,7 +1367,7 @@ struct b200bpe {
     uint64_t table_bytes[4] = {0, 0, 0, 0};
     static const int N_SLOTS = 3;
     Slot slots[3];
-    float last_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    float last_ms[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
     uint32_t last_launches = 0;
     size_t chunk_bytes = 64u << 20;
     std::mutex mu;
@@ -1582,6 +1585,7 @@ static int run_pipeline(b200bpe *h, Slot &S, const uint8_t *d_text, uint64_t n_b
         p.out = d_out; p.tok_off = d_tok_off; p.ctr = S.d_ctr;
         p.big_dst = S.w_big_dst.p; p.big_src = S.w_big_src.p; p.big_n = S.w_big_n.p;
         probe_kernel<<<(unsigned)((n_tiles + ENC_WARPS - 1) / ENC_WARPS), ENC_WARPS * 32, 0, st>>>(p, h->T);
+        CUDA_TRY(cudaEventRecord(S.ev[8], st));
         miss_hist_kernel<<<SORT_BLOCKS, 256, 0, st>>>(p, S.w_sort_hist.p);
         miss_base_kernel<<<1, 17 * 32, 0, st>>>(S.w_sort_hist.p, SORT_BLOCKS);
         miss_scatter_kernel<<<SORT_BLOCKS, 256, 0, st>>>(p, S.w_sort_hist.p);
@@ -1614,6 +1618,7 @@ static int finish_pipeline(b200bpe *h, Slot &S, cudaStream_t st) {
     cudaEventElapsedTime(&S.last_ms[2], S.ev[2], S.ev[3]);
     cudaEventElapsedTime(&S.last_ms[3], S.ev[3], S.ev[7]);
     cudaEventElapsedTime(&S.last_ms[7], S.ev[7], S.ev[4]);
+    cudaEventElapsedTime(&S.last_ms[8], S.ev[3], S.ev[8]);
     cudaEventElapsedTime(&S.last_ms[4], S.ev[0], S.ev[4]);
     if (S.h_ctr->err & ERR_DOCOFF)
         return fail(B200BPE_EINVAL, "document offsets must start at 0, be non-decreasing and end at n_bytes");
@@ -1697,7 +1702,7 @@ static int encode_host(b200bpe *h, const uint8_t *text, const uint64_t *doc_off,
         return B200BPE_OK;
     };
 
-    float sum_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0}; uint32_t launches = 0;
+    float sum_ms[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}; uint32_t launches = 0;
     uint64_t token_base = 0;
     // finalise chunk c: wait for its kernels, then send its offsets + tokens home (async)
     auto drain = [&](size_t c) -> int {
@@ -1722,7 +1727,7 @@ static int encode_host(b200bpe *h, const uint8_t *text, const uint64_t *doc_off,
         CUDA_TRY(cudaEventRecord(S.ev[6], S.stream));
         token_base += nt;
         for (int i = 0; i < 5; i++) sum_ms[i] += S.last_ms[i];
-        sum_ms[7] += S.last_ms[7]; sum_ms[5] += h2d; launches += S.last_launches;
+        sum_ms[7] += S.last_ms[7]; sum_ms[8] += S.last_ms[8]; sum_ms[5] += h2d; launches += S.last_launches;
         return B200BPE_OK;
     };
     auto fail_all = [&](int rc2) {
@@ -1934,9 +1939,9 @@ extern "C" int b200bpe_decode_batch(b200bpe_t *h, const uint32_t *tokens, const 
     return B200BPE_OK;
 }
 
-extern "C" int b200bpe_last_timings(b200bpe_t *h, float *ms8, uint32_t *n_launches) {
+extern "C" int b200bpe_last_timings(b200bpe_t *h, float *ms9, uint32_t *n_launches) {
     if (!h) return fail(B200BPE_EINVAL, "null handle");
-    if (ms8) memcpy(ms8, h->last_ms, sizeof(h->last_ms));
+    if (ms9) memcpy(ms9, h->last_ms, sizeof(h->last_ms));
     if (n_launches) *n_launches = h->last_launches;
     return B200BPE_OK;
 }
