@@ -48,3 +48,33 @@ def test_product_package_does_not_import_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
                 src = open(os.path.join(dirpath, f), errors="replace").read()
                 assert "import oracle" not in src and "from oracle" not in src and "liboracle" not in src, f
+
+
+def test_pack_helper_matches_python_marshalling():
+    """csrc/pack_ext.c (list[str] -> packed UTF-8 + offsets, token buffers -> list[list[int]])
+    agrees with the pure-Python marshalling, including the UnicodeEncodeError on lone surrogates
+    that tiktoken/core.py:77,128 relies on."""
+    import numpy as np
+    import __graft_entry__  # noqa: F401  (sys.path)
+    from tiktoken_b200 import _tiktoken as T
+    if T._b200pack is None:
+        import __graft_entry__ as g
+        g.build()
+        import importlib
+        importlib.reload(T)
+    assert T._b200pack is not None
+    docs = ["", "hello", "héllo 日本", "", "\U0001F600 x" * 50, "a" * 100000]
+    arr, off = T.CoreBPE._pack(docs)
+    enc = [d.encode() for d in docs]
+    assert arr.tobytes() == b"".join(enc)
+    assert off.tolist() == np.concatenate([[0], np.cumsum([len(e) for e in enc])]).tolist()
+    arr0, off0 = T.CoreBPE._pack([])
+    assert off0.tolist() == [0]
+    with pytest.raises(UnicodeEncodeError):
+        T.CoreBPE._pack(["ok", "\ud83d"])
+    with pytest.raises(TypeError):
+        T._b200pack.pack([b"bytes"])
+    toks = (np.arange(10, dtype=np.uint64) * 400000003 % (1 << 32)).astype(np.uint32)
+    toff = np.asarray([0, 0, 3, 3, 10], np.uint64)
+    got = T._b200pack.unpack(toks.ctypes.data, toff.ctypes.data, 4)
+    assert got == [[], toks[:3].tolist(), [], toks[3:].tolist()]

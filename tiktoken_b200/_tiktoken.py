@@ -15,6 +15,11 @@ import numpy as np
 
 from . import _lib
 
+try:                                    # C marshalling helper (csrc/pack_ext.c), built by __graft_entry__.build()
+    from . import _b200pack
+except ImportError:                     # host marshalling only -- the kernels never depend on it
+    _b200pack = None
+
 
 def _ptr(a: np.ndarray):
     return C.c_void_p(a.ctypes.data)
@@ -114,11 +119,21 @@ class CoreBPE:
 
     @staticmethod
     def _pack(texts: list[str]):
-        enc = [t.encode("utf-8") for t in texts]      # UnicodeEncodeError on lone surrogates, like &str extraction
+        """list[str] -> (uint8 blob, uint64 offsets); UnicodeEncodeError on lone surrogates, like the
+        `&str` extraction of py.rs:30,36 (core.py:77,128 catch it and retry)."""
+        if _b200pack is not None:
+            blob, offs = _b200pack.pack(texts)
+            arr = np.frombuffer(blob, dtype=np.uint8) if blob else np.zeros(1, np.uint8)
+            return arr, np.frombuffer(offs, dtype=np.uint64)
+        enc = [t.encode("utf-8") for t in texts]
         return _flatten_bytes(enc)
 
     @staticmethod
     def _unpack(buf: TokenBuffer) -> list[list[int]]:
+        if _b200pack is not None and buf.n_tokens:
+            out = _b200pack.unpack(buf.tokens().ctypes.data, buf.offsets().ctypes.data, buf.n_docs)
+            buf.close()
+            return out
         toks = buf.tokens().tolist()
         off = buf.offsets().tolist()
         out = [toks[off[i]:off[i + 1]] for i in range(buf.n_docs)]
