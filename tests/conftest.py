@@ -34,6 +34,13 @@ def hostcheck():
     H.hc_tables_new.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]
     H.hc_tables_free.argtypes = [C.c_void_p]
     H.hc_encode_short.argtypes = [C.c_void_p, C.c_char_p, C.c_uint32, C.c_void_p]
+    H.hc_encode_mid.argtypes = [C.c_void_p, C.c_char_p, C.c_uint32, C.c_uint32, C.c_void_p]
+    H.hc_pair_lookup.restype = C.c_uint32
+    H.hc_pair_lookup.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32]
+    H.hc_pair_buckets.restype = C.c_uint64
+    H.hc_pair_buckets.argtypes = [C.c_void_p]
+    H.hc_tables_pairs.restype = C.c_uint64
+    H.hc_tables_pairs.argtypes = [C.c_void_p]
     H.hc_probe_long.restype = C.c_uint32
     H.hc_probe_long.argtypes = [C.c_void_p, C.c_char_p, C.c_uint32]
     return H

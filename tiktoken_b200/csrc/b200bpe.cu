@@ -59,8 +59,8 @@ struct Counters {            // device-resident, zeroed per call
     unsigned long long long_bytes;
     unsigned int n_long;
     unsigned int long_head;
-    unsigned int giant_head;
-    unsigned int n_giant;
+    unsigned int n_cls[6];           // long pieces per length class (see LongQ::cls)
+    unsigned int cls_head[6];        // work-queue heads of the per-class kernels
     unsigned int n_big;
     unsigned int n_miss;
     unsigned long long miss_bytes;
@@ -72,14 +72,22 @@ struct Counters {            // device-resident, zeroed per call
 };
 
 static const uint32_t GIANT_MIN = 4096;      // pieces longer than this get a whole block (kernel 3b)
-static const uint32_t LONG_SCRATCH_MIN = 256; // pieces longer than this merge in global scratch (= MID_MAX)
+static const uint32_t LONG_SCRATCH_MIN = 256; // pieces longer than this merge in global scratch (warp / block per piece)
 
 struct LongQ {               // queue of pieces longer than SHORT_MAX bytes
     unsigned long long *start;   // byte offset of the piece
     unsigned int *len;
     unsigned long long *off;     // offset of its region in the global merge scratch (pieces > LONG_SCRATCH_MIN only)
     unsigned int *ntok;
-    unsigned int *giant;         // indices (into this queue) of the pieces longer than GIANT_MIN
+    // indices (into this queue) per length class: 0: 17..32, 1: 33..64, 2: 65..128, 3: 129..256 bytes
+    // (thread-per-piece kernels), 4: 257..GIANT_MIN (warp per piece), 5: longer (block per piece)
+    unsigned int *cls[6];
+};
+static const int N_CLS = 6, CLS_WARP = 4, CLS_GIANT = 5;
+
+struct SmemCol32 {           // per-lane column of a [k][32] shared-memory array: bank == lane whatever k is
+    uint32_t *base;
+    __device__ __forceinline__ uint32_t &operator[](int j) const { return base[j * 32]; }
 };
 
 // --------------------------------------------------------------------------------------------
@@ -184,7 +192,15 @@ __global__ void __launch_bounds__(256) find_long_kernel(const uint32_t *__restri
             if (len > LONG_SCRATCH_MIN) off = atomicAdd(&ctr->long_bytes, (unsigned long long)len);
             q.start[i] = (unsigned long long)s; q.len[i] = (unsigned int)len; q.off[i] = off;
             lidx[s >> 4] = i;
-            if (len > GIANT_MIN) q.giant[atomicAdd(&ctr->n_giant, 1u)] = i;
+            // per-class work list, one atomic per (warp iteration, class)
+            const int c = len > GIANT_MIN ? CLS_GIANT : len > 256 ? CLS_WARP : len > 128 ? 3 : len > 64 ? 2 : len > 32 ? 1 : 0;
+            const uint32_t same = __match_any_sync(peers, c);
+            unsigned int k = 0;
+            if ((threadIdx.x & 31) == __ffs(same) - 1) k = atomicAdd(&ctr->n_cls[c], (unsigned int)__popc(same));
+            k = __shfl_sync(peers, k, __ffs(same) - 1) + __popc(same & ((1u << (threadIdx.x & 31)) - 1u));
+            // (constant indices: a dynamically indexed kernel parameter would be copied to local memory by every thread)
+            unsigned int *lst = c == 0 ? q.cls[0] : c == 1 ? q.cls[1] : c == 2 ? q.cls[2] : c == 3 ? q.cls[3] : c == 4 ? q.cls[4] : q.cls[5];
+            lst[k] = i;
         }
     }
 }
@@ -332,262 +348,25 @@ __device__ uint32_t long_piece_warp(const DevTables &T, const uint8_t *__restric
     return m;
 }
 
-// --------------------------------------------------------------------------------------------
-// Mid-size pieces (17..256 bytes: CJK runs, indentation, separators, long words): one warp per
-// piece with the parts held in REGISTERS, part p = slot*32 + lane (8 slots).  One merge per
-// round -- the literal min-rank loop of src/lib.rs:140-196 -- but a round is ~100 instructions
-// and ONE L2 latency: argmin by two hardware warp reductions (redux.sync), neighbours from the
-// alive bitmap (uniform bit scans), the two neighbour probes issued side by side by two lanes.
-// --------------------------------------------------------------------------------------------
-static const int MID_SLOTS = 8;
-static const uint32_t MID_MAX = MID_SLOTS * 32;
-
-struct MidSmem {                       // per-warp merge state: part p = slot*32 + lane -> conflict-free columns
-    uint32_t id[MID_MAX];
-    uint32_t rk[MID_MAX];
-    uint32_t am[MID_SLOTS];            // alive bitmap
-};
-
-// next / previous alive part.  The neighbour is almost always in the same 32-part word, so the
-// common case is one shared load + one bit scan (all lanes compute the same, uniform, value).
-__device__ __forceinline__ int next_alive(const uint32_t *am, int p, int n_slots) {
-    const int w0 = p >> 5, b = p & 31;
-    uint32_t m = (b == 31) ? 0u : (am[w0] & ~((2u << b) - 1u));
-    if (m) return w0 * 32 + __ffs(m) - 1;
-    for (int w = w0 + 1; w < n_slots; w++) { m = am[w]; if (m) return w * 32 + __ffs(m) - 1; }
-    return -1;
-}
-__device__ __forceinline__ int prev_alive(const uint32_t *am, int p) {
-    const int w0 = p >> 5, b = p & 31;
-    uint32_t m = am[w0] & ((1u << b) - 1u);
-    if (m) return w0 * 32 + 31 - __clz((int)m);
-    for (int w = w0 - 1; w >= 0; w--) { m = am[w]; if (m) return w * 32 + 31 - __clz((int)m); }
-    return -1;
-}
-
-__device__ uint32_t mid_piece_warp(const DevTables &T, const uint8_t *__restrict__ piece, uint32_t n, MidSmem &M,
-                                   uint32_t *__restrict__ out, uint32_t *err) {
-    const int lane = threadIdx.x & 31;
-    const uint32_t FULL = 0xFFFFFFFFu;
-    // whole-piece probe (src/lib.rs:367-368); only a token of exactly this length can match
-    if (n <= T.max_token_len && T.n_long_tokens) {
-        uint64_t hw = 0;                                     // one 8-byte word per lane (n <= 256)
-        if ((uint32_t)lane * 8u < n) {
-            uint64_t w = 0;
-            for (uint32_t k = 0; k < 8 && (uint32_t)lane * 8u + k < n; k++) w |= (uint64_t)piece[lane * 8 + k] << (8 * k);
-            hw = long_hash_word(w, (uint32_t)lane);
-        }
-        const uint32_t hlo = __reduce_xor_sync(FULL, (uint32_t)hw), hhi = __reduce_xor_sync(FULL, (uint32_t)(hw >> 32));
-        uint32_t r = RANK_MAX;
-        if (lane == 0) r = piece_lookup_long(T, long_hash_init(n) ^ (((uint64_t)hhi << 32) | hlo), n, [&](uint32_t i) { return piece[i]; });
-        r = __shfl_sync(FULL, r, 0);
-        if (r != RANK_MAX) { if (lane == 0) out[0] = r; return 1; }
-    }
-    const int n_slots = (int)((n + 31) >> 5);
-    for (int s = 0; s < n_slots; s++) {
-        const uint32_t p = (uint32_t)s * 32u + (uint32_t)lane;
-        uint32_t i0 = 0, r0 = RANK_MAX;
-        if (p < n) {
-            const uint32_t b = piece[p];
-            i0 = __ldg(T.byte_id + b);
-            if (p + 1 < n) r0 = __ldg(T.pair2 + ((b << 8) | piece[p + 1]));
-        }
-        M.id[p] = i0; M.rk[p] = r0;
-        const uint32_t al = __ballot_sync(FULL, p < n);
-        if (lane == 0) M.am[s] = al;
-    }
-    __syncwarp();
-    for (;;) {
-        uint32_t best = RANK_MAX, bp = 0xFFFFu;
-        for (int s = 0; s < n_slots; s++) {
-            const uint32_t r = M.rk[s * 32 + lane];
-            if (r < best) { best = r; bp = (uint32_t)s * 32u + (uint32_t)lane; }
-        }
-        const uint32_t g = __reduce_min_sync(FULL, best);
-        if (g == RANK_MAX) break;
-        const int bj = (int)__reduce_min_sync(FULL, best == g ? bp : 0xFFFFFFFFu);   // leftmost on ties
-        const int j2 = next_alive(M.am, bj, n_slots);        // right part of the merged pair
-        int j3 = -1;                                         // part after j2 (the new right neighbour)
-        {
-            const int w2 = j2 >> 5, b2 = j2 & 31;
-            uint32_t m = (b2 == 31) ? 0u : (M.am[w2] & ~((2u << b2) - 1u));
-            if (m) j3 = w2 * 32 + __ffs(m) - 1;
-            else for (int w = w2 + 1; w < n_slots; w++) { m = M.am[w]; if (m) { j3 = w * 32 + __ffs(m) - 1; break; } }
-        }
-        const int jp = prev_alive(M.am, bj);
-        uint32_t r = RANK_MAX;
-        {   // lane 0 probes (merged, right neighbour), lane 1 (left neighbour, merged): one call site, one latency
-            const int jn = lane == 0 ? j3 : jp;
-            if (lane < 2 && jn >= 0) {
-                const uint32_t o = M.id[jn];
-                r = pair_lookup(T, lane == 0 ? g : o, lane == 0 ? o : g);
-            }
-        }
-        const uint32_t rr = __shfl_sync(FULL, r, 0), rl = __shfl_sync(FULL, r, 1);
-        if (lane == 0) {
-            M.id[bj] = g; M.rk[bj] = (j3 >= 0) ? rr : RANK_MAX; M.rk[j2] = RANK_MAX;
-            if (jp >= 0) M.rk[jp] = rl;
-            M.am[j2 >> 5] &= ~(1u << (j2 & 31));
-        }
-        __syncwarp();
-    }
-    uint32_t cnt = 0; bool bad = false;
-    for (int s = 0; s < n_slots; s++) {
-        const uint32_t m = M.am[s];
-        if ((m >> lane) & 1u) {
-            const uint32_t x = M.id[s * 32 + lane];
-            out[cnt + __popc(m & ((1u << lane) - 1u))] = x;
-            bad |= x >= PSEUDO_BASE;
-        }
-        cnt += __popc(m);
-    }
-    if (__any_sync(FULL, bad) && lane == 0) atomicOr(err, ERR_NOBYTE);
-    __syncwarp();
-    return cnt;
-}
-
-// Two pieces per warp for the bulk of the mid-size class (17..128 bytes): each HALF-warp owns one
-// piece (part p = slot*16 + lane_in_half, <= 8 slots) and both halves walk the same instruction
-// stream, so an instruction serves two merges.  Same algorithm and data layout as mid_piece_warp;
-// the group primitives (redux.sync / shfl) simply run on the half-warp masks.
-static const uint32_t PAIR_MAX = 128;
-
-__device__ void mid_piece_pair(const DevTables &T, const uint8_t *__restrict__ piece, uint32_t n /* 0 = idle half */,
-                               MidSmem &M, uint32_t *__restrict__ out, uint32_t *ntok_out, uint32_t *err) {
-    const int lane = threadIdx.x & 31, half = lane >> 4, hl = lane & 15;
-    const uint32_t gmask = half ? 0xFFFF0000u : 0x0000FFFFu;
-    const int lead = half * 16;
-    uint32_t *id = M.id + half * PAIR_MAX, *rk = M.rk + half * PAIR_MAX;       // MidSmem holds 256 parts: 128 per half
-    uint32_t *am = M.am + half * 4;                                          // 8 x 16-bit alive words per half
-    uint16_t *am16 = reinterpret_cast<uint16_t *>(am);
-    bool active = n != 0;
-    // whole-piece probe by the first lane of each half
-    if (active && n <= T.max_token_len && T.n_long_tokens) {
-        uint64_t hw = 0;                                     // one 8-byte word per lane of the half (n <= 128)
-        if ((uint32_t)hl * 8u < n) {
-            uint64_t w = 0;
-            for (uint32_t k = 0; k < 8 && (uint32_t)hl * 8u + k < n; k++) w |= (uint64_t)piece[hl * 8 + k] << (8 * k);
-            hw = long_hash_word(w, (uint32_t)hl);
-        }
-        const uint32_t hlo = __reduce_xor_sync(gmask, (uint32_t)hw), hhi = __reduce_xor_sync(gmask, (uint32_t)(hw >> 32));
-        uint32_t r = RANK_MAX;
-        if (hl == 0) r = piece_lookup_long(T, long_hash_init(n) ^ (((uint64_t)hhi << 32) | hlo), n, [&](uint32_t i) { return piece[i]; });
-        r = __shfl_sync(gmask, r, lead);
-        if (r != RANK_MAX) { if (hl == 0) { out[0] = r; *ntok_out = 1; } active = false; n = 0; }
-    }
-    const int n_slots = (int)((n + 15) >> 4);
-    for (int s = 0; s < 8; s++) {
-        const uint32_t p = (uint32_t)s * 16u + (uint32_t)hl;
-        uint32_t i0 = 0, r0 = RANK_MAX;
-        if (p < n) {
-            const uint32_t b = piece[p];
-            i0 = __ldg(T.byte_id + b);
-            if (p + 1 < n) r0 = __ldg(T.pair2 + ((b << 8) | piece[p + 1]));
-        }
-        id[p] = i0; rk[p] = r0;
-        const uint32_t al = __ballot_sync(0xFFFFFFFFu, p < n);
-        if (hl == 0) am16[s] = (uint16_t)(al >> lead);
-    }
-    __syncwarp();
-    auto next_al = [&](int p) -> int {                        // next alive part after p (same value in all lanes of the half)
-        const int w0 = p >> 4, b = p & 15;
-        uint32_t m = (uint32_t)am16[w0] & ~((2u << b) - 1u) & 0xFFFFu;
-        if (m) return w0 * 16 + __ffs(m) - 1;
-        for (int w = w0 + 1; w < 8; w++) { m = am16[w]; if (m) return w * 16 + __ffs(m) - 1; }
-        return -1;
-    };
-    auto prev_al = [&](int p) -> int {
-        const int w0 = p >> 4, b = p & 15;
-        uint32_t m = (uint32_t)am16[w0] & ((1u << b) - 1u);
-        if (m) return w0 * 16 + 31 - __clz((int)m);
-        for (int w = w0 - 1; w >= 0; w--) { m = am16[w]; if (m) return w * 16 + 31 - __clz((int)m); }
-        return -1;
-    };
-    while (__any_sync(0xFFFFFFFFu, active)) {
-        uint32_t best = RANK_MAX, bp = 0xFFFFu;
-        for (int s = 0; s < n_slots; s++) {
-            const uint32_t r = rk[s * 16 + hl];
-            if (r < best) { best = r; bp = (uint32_t)s * 16u + (uint32_t)hl; }
-        }
-        const uint32_t g = __reduce_min_sync(gmask, best);
-        const int bj = (int)__reduce_min_sync(gmask, best == g ? bp : 0xFFFFFFFFu);   // leftmost on ties
-        if (g == RANK_MAX) active = false;
-        int j2 = -1, j3 = -1, jp = -1;
-        if (active) { j2 = next_al(bj); j3 = next_al(j2); jp = prev_al(bj); }
-        uint32_t r = RANK_MAX;
-        {   // lane 0 of the half probes (merged, right neighbour), lane 1 (left neighbour, merged)
-            const int jn = hl == 0 ? j3 : jp;
-            if (active && hl < 2 && jn >= 0) {
-                const uint32_t o = id[jn];
-                r = pair_lookup(T, hl == 0 ? g : o, hl == 0 ? o : g);
-            }
-        }
-        const uint32_t rr = __shfl_sync(gmask, r, lead), rl = __shfl_sync(gmask, r, lead + 1);
-        if (active && hl == 0) {
-            id[bj] = g; rk[bj] = (j3 >= 0) ? rr : RANK_MAX; rk[j2] = RANK_MAX;
-            if (jp >= 0) rk[jp] = rl;
-            am16[j2 >> 4] &= (uint16_t)~(1u << (j2 & 15));
-        }
-        __syncwarp();
-    }
-    if (n) {
-        uint32_t cnt = 0; bool bad = false;
-        for (int s = 0; s < n_slots; s++) {
-            const uint32_t m = am16[s];
-            if ((m >> hl) & 1u) {
-                const uint32_t x = id[s * 16 + hl];
-                out[cnt + __popc(m & ((1u << hl) - 1u))] = x;
-                bad |= x >= PSEUDO_BASE;
-            }
-            cnt += __popc(m);
-        }
-        if (bad) atomicOr(err, ERR_NOBYTE);
-        if (hl == 0) *ntok_out = cnt;
-    }
-    __syncwarp();
-}
-
 static const int LONG_WARPS = 8;               // warps per block of long_piece_kernel
 
 __global__ void __launch_bounds__(LONG_WARPS * 32) long_piece_kernel(const uint8_t *__restrict__ text, DevTables T, LongQ q,
                                                                     LongScratch S, uint32_t *ltok, Counters *ctr) {
-    __shared__ MidSmem s_mid[LONG_WARPS];
-    const int lane = threadIdx.x & 31, half = lane >> 4;
-    const unsigned int n_long = ctr->n_long;
+    const int lane = threadIdx.x & 31;
+    const unsigned int n_long = ctr->n_cls[CLS_WARP];
+    const unsigned int *list = q.cls[CLS_WARP];
     for (;;) {
-        unsigned int i0 = 0;
-        if (lane == 0) i0 = atomicAdd(&ctr->long_head, 2u);
-        i0 = __shfl_sync(0xFFFFFFFFu, i0, 0);
-        if (i0 >= n_long) break;
-        const unsigned int i1 = i0 + 1;
-        const uint32_t len0 = q.len[i0], len1 = i1 < n_long ? q.len[i1] : 0u;
-        MidSmem &M = s_mid[threadIdx.x >> 5];
-        // two pieces of <= 128 bytes: one per half-warp, in lockstep
-        const bool pair0 = len0 <= PAIR_MAX, pair1 = len1 != 0 && len1 <= PAIR_MAX;
-        if (pair0 || pair1) {
-            const unsigned int mi = half ? i1 : i0;
-            const bool mine = half ? pair1 : pair0;
-            const unsigned long long st0 = mine ? q.start[mi] : 0ull;
-            uint32_t nt = 0;
-            mid_piece_pair(T, text + st0, mine ? (half ? len1 : len0) : 0u, M, ltok + st0, &nt, &ctr->err);
-            if (mine && (lane & 15) == 0) q.ntok[mi] = nt;
-            __syncwarp();
-        }
-        for (int k = 0; k < 2; k++) {                           // the rest: whole warp, one after the other
-            const unsigned int i = k ? i1 : i0;
-            const uint32_t len = k ? len1 : len0;
-            if (len == 0 || len <= PAIR_MAX || len > GIANT_MIN) continue;   // giant pieces: giant_piece_kernel
-            const unsigned long long off = q.off[i], st0 = q.start[i];
-            uint32_t nt;
-            if (len <= MID_MAX) nt = mid_piece_warp(T, text + st0, len, M, ltok + st0, &ctr->err);
-            else {
-                LongScratch P = S;
-                P.idA += off; P.rkA += off; P.idB += off; P.rkB += off; P.aux1 += off; P.aux2 += off; P.flag += off;
-                nt = long_piece_warp(T, text + st0, len, P, ltok + st0, &ctr->err);
-            }
-            if (lane == 0) q.ntok[i] = nt;
-            __syncwarp();
-        }
+        unsigned int k = 0;
+        if (lane == 0) k = atomicAdd(&ctr->cls_head[CLS_WARP], 1u);
+        k = __shfl_sync(0xFFFFFFFFu, k, 0);
+        if (k >= n_long) break;
+        const unsigned int i = list[k];
+        const unsigned long long off = q.off[i], st0 = q.start[i];
+        LongScratch P = S;
+        P.idA += off; P.rkA += off; P.idB += off; P.rkB += off; P.aux1 += off; P.aux2 += off; P.flag += off;
+        const uint32_t nt = long_piece_warp(T, text + st0, q.len[i], P, ltok + st0, &ctr->err);
+        if (lane == 0) q.ntok[i] = nt;
+        __syncwarp();
     }
 }
 
@@ -741,19 +520,104 @@ __device__ uint32_t long_piece_block(const DevTables &T, const uint8_t *__restri
 __global__ void __launch_bounds__(GIANT_THREADS) giant_piece_kernel(const uint8_t *__restrict__ text, DevTables T, LongQ q,
                                                                     LongScratch S, uint32_t *ltok, Counters *ctr) {
     __shared__ unsigned int s_i;
-    const unsigned int n_giant = ctr->n_giant;
+    const unsigned int n_giant = ctr->n_cls[CLS_GIANT];
     for (;;) {
         __syncthreads();
-        if (threadIdx.x == 0) s_i = atomicAdd(&ctr->giant_head, 1u);
+        if (threadIdx.x == 0) s_i = atomicAdd(&ctr->cls_head[CLS_GIANT], 1u);
         __syncthreads();
         if (s_i >= n_giant) break;
-        const unsigned int i = q.giant[s_i];
+        const unsigned int i = q.cls[CLS_GIANT][s_i];
         const unsigned long long off = q.off[i];
         LongScratch P = S;
         P.idA += off; P.rkA += off; P.idB += off; P.rkB += off; P.aux1 += off; P.aux2 += off; P.flag += off;
         const uint32_t nt = long_piece_block(T, text + q.start[i], q.len[i], P, ltok + q.start[i], &ctr->err);
         if (threadIdx.x == 0) q.ntok[i] = nt;
     }
+}
+
+// --------------------------------------------------------------------------------------------
+// kernel 3a: mid-size pieces (17..256 bytes: CJK runs, indentation, separators, long words), ONE
+// PIECE PER LANE.  find_long_kernel sorts the pieces into length classes of capacity 32 / 64 / 128 /
+// 256 parts; a warp merges 32 pieces of one class at a time, walking one convergent instruction
+// stream (merge_short_conv for 32, merge_mid_conv above that): the cost of a merge round is shared
+// by 32 pieces instead of being paid per piece as in the warp-per-piece kernels.
+// State: two [CAP][32] shared-memory columns per warp (id, rank) + the two-level minimum, conflict
+// free for any per-lane index.  One launch serves the four classes, longest first: a block owns
+// MID_SMEM_BYTES of columns, enough for 256 / CAP warps of a class, and moves to the next class (a
+// block-local barrier, no kernel boundary) when the class's work list is drained.
+// --------------------------------------------------------------------------------------------
+static const int MID_WARPS = 8;                                  // 8 x 32 = 256 parts x 32 lanes per block
+static const size_t MID_SMEM_BYTES = (size_t)2 * (256 + 256 / MID_G) * 32 * sizeof(uint32_t);
+
+template <int CAP>
+__device__ void mid_class(const uint8_t *__restrict__ text, const DevTables &T, const LongQ &q, int cls, uint32_t *ltok,
+                          Counters *ctr, uint32_t *s_cols) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (warp >= 256 / CAP) return;                             // the block's columns hold 256 / CAP warps of this class
+    const int per_warp = CAP == 32 ? 2 * CAP * 32 : 2 * (CAP + CAP / MID_G) * 32;
+    uint32_t *base = s_cols + (size_t)warp * per_warp;
+    SmemCol32 id{base + lane}, rk{base + CAP * 32 + lane};
+    SmemCol32 gmin{base + 2 * CAP * 32 + lane}, gpos{base + (2 * CAP + CAP / MID_G) * 32 + lane};
+    const unsigned int n_items = ctr->n_cls[cls];
+    const unsigned int *list = q.cls[cls];
+    for (;;) {
+        unsigned int k0 = 0;
+        if (lane == 0) k0 = atomicAdd(&ctr->cls_head[cls], 32u);
+        k0 = __shfl_sync(0xFFFFFFFFu, k0, 0);
+        if (k0 >= n_items) break;
+        const bool have = k0 + lane < n_items;
+        unsigned int qi = 0; unsigned long long st = 0; int n = 0;
+        if (have) { qi = list[k0 + lane]; st = q.start[qi]; n = (int)q.len[qi]; }
+        const uint8_t *piece = text + st;
+        uint32_t *out = ltok + st;
+        int n_max = (int)__reduce_max_sync(0xFFFFFFFFu, (unsigned)n);
+        // stage the bytes (column rk doubles as the byte buffer until the merge initialises it)
+        for (int j = 0; j < n_max; j++) rk[j] = j < n ? (uint32_t)piece[j] : 0u;
+        // whole-piece probe (src/lib.rs:367-368): only a token of exactly this length can match
+        if (have && (uint32_t)n <= T.max_token_len && T.n_long_tokens) {
+            uint64_t h = long_hash_init((uint64_t)n);
+            for (int i = 0; i < n; i += 8) {
+                uint64_t w = 0;
+                for (int k = 0; k < 8 && i + k < n; k++) w |= (uint64_t)rk[i + k] << (8 * k);
+                h = long_hash_step(h, w, (uint32_t)(i >> 3));
+            }
+            const uint32_t r = piece_lookup_long(T, h, (uint32_t)n, [&](uint32_t i) { return piece[i]; });
+            if (r != RANK_MAX) { out[0] = r; q.ntok[qi] = 1; n = 0; }
+        }
+        n_max = (int)__reduce_max_sync(0xFFFFFFFFu, (unsigned)n);
+        if (n_max) {
+            uint32_t c = 0; bool bad = false;
+            if (CAP == 32) {
+                const uint32_t mask = merge_short_conv(T, [&](int j) { return rk[j]; }, n, n_max, 0xFFFFFFFFu, id, rk);
+                for (uint32_t mm = mask; mm;) {
+                    const int j = __ffs(mm) - 1; mm &= mm - 1;
+                    const uint32_t x = id[j];
+                    out[c++] = x; bad |= x >= PSEUDO_BASE;
+                }
+            } else {
+                merge_mid_conv(T, n, n_max, 0xFFFFFFFFu, id, rk, gmin, gpos);
+                for (int j = 0; j < n; j++) {
+                    const uint32_t x = id[j];
+                    if (x != ID_DEAD) { out[c++] = x; bad |= x >= PSEUDO_BASE; }
+                }
+            }
+            if (n) q.ntok[qi] = c;
+            if (bad) atomicOr(&ctr->err, ERR_NOBYTE);
+        }
+        __syncwarp();
+    }
+}
+
+__global__ void __launch_bounds__(MID_WARPS * 32) mid_thread_kernel(const uint8_t *__restrict__ text, DevTables T, LongQ q,
+                                                                   uint32_t *ltok, Counters *ctr) {
+    extern __shared__ uint32_t s_cols[];
+    mid_class<256>(text, T, q, 3, ltok, ctr, s_cols);
+    __syncthreads();
+    mid_class<128>(text, T, q, 2, ltok, ctr, s_cols);
+    __syncthreads();
+    mid_class<64>(text, T, q, 1, ltok, ctr, s_cols);
+    __syncthreads();
+    mid_class<32>(text, T, q, 0, ltok, ctr, s_cols);
 }
 
 // --------------------------------------------------------------------------------------------
@@ -970,10 +834,6 @@ struct MissSmem {
     uint32_t id[SHORT_MAX * 32];       // [part][lane]
     uint32_t rk[SHORT_MAX * 32];
     uint32_t bytes[4 * 32];            // [word][lane]: the piece bytes, little-endian
-};
-struct SmemCol32 {
-    uint32_t *base;
-    __device__ __forceinline__ uint32_t &operator[](int j) const { return base[j * 32]; }
 };
 
 // counting sort of the miss queue by piece length (so that a warp merges pieces of one length):
@@ -1310,7 +1170,7 @@ struct Slot {
     DevBuf<uint8_t> w_text; DevBuf<unsigned long long> w_docoff, w_tokoff, w_sub_base;
     DevBuf<uint32_t> w_ptok, w_mres, w_mq_pos, w_mq_roff, w_mq_order, w_sub_count; DevBuf<uint8_t> w_mq_len, w_mq_cnt;
     DevBuf<uint32_t> w_dbits, w_pbits, w_psum, w_sfd, w_lidx, w_out, w_ltok;
-    DevBuf<unsigned long long> w_lq_start, w_lq_off; DevBuf<unsigned int> w_lq_len, w_lq_ntok, w_lq_giant, w_big_n, w_sort_hist; DevBuf<unsigned long long> w_big_dst, w_big_src, w_scan_part;
+    DevBuf<unsigned long long> w_lq_start, w_lq_off; DevBuf<unsigned int> w_lq_len, w_lq_ntok, w_lq_cls, w_big_n, w_sort_hist; DevBuf<unsigned long long> w_big_dst, w_big_src, w_scan_part;
     DevBuf<uint32_t> w_idA, w_rkA, w_idB, w_rkB, w_aux1, w_aux2; DevBuf<uint8_t> w_flag;
     Counters *d_ctr = nullptr; Counters *h_ctr = nullptr;   // h_ctr pinned
     cudaStream_t stream = nullptr;
@@ -1332,7 +1192,7 @@ struct Slot {
         w_ptok.release(); w_mres.release(); w_mq_pos.release(); w_mq_roff.release(); w_mq_order.release(); w_sub_count.release();
         w_mq_len.release(); w_mq_cnt.release();
         w_dbits.release(); w_pbits.release(); w_psum.release(); w_sfd.release(); w_lidx.release(); w_out.release(); w_ltok.release();
-        w_lq_start.release(); w_lq_off.release(); w_lq_len.release(); w_lq_ntok.release(); w_lq_giant.release(); w_big_n.release(); w_sort_hist.release(); w_big_dst.release(); w_big_src.release(); w_scan_part.release();
+        w_lq_start.release(); w_lq_off.release(); w_lq_len.release(); w_lq_ntok.release(); w_lq_cls.release(); w_big_n.release(); w_sort_hist.release(); w_big_dst.release(); w_big_src.release(); w_scan_part.release();
         w_idA.release(); w_rkA.release(); w_idB.release(); w_rkB.release(); w_aux1.release(); w_aux2.release();
         w_flag.release();
         if (d_ctr) cudaFree(d_ctr);
@@ -1456,6 +1316,7 @@ extern "C" int b200bpe_create(const uint8_t *tok_bytes, const uint64_t *tok_off,
         if (e == cudaSuccess) e = upload(&h->d_tok_blob, blob.data(), blob.size());
     }
     for (int i = 0; i < b200bpe::N_SLOTS && e == cudaSuccess; i++) e = h->slots[i].init();
+    CUDA_TRY(cudaFuncSetAttribute(mid_thread_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MID_SMEM_BYTES));
     if (const char *cm = getenv("B200BPE_CHUNK_MB")) { long v = atol(cm); if (v >= 1 && v <= 2048) h->chunk_bytes = (size_t)v << 20; }
     if (e != cudaSuccess) { std::string m = cudaGetErrorString(e); delete h; return fail(B200BPE_ECUDA, "table upload: " + m); }
     h->T.byte_id = h->d_byte_id; h->T.pair2 = h->d_pair2;
@@ -1516,10 +1377,19 @@ static int run_pipeline(b200bpe *h, Slot &S, const uint8_t *d_text, uint64_t n_b
     const size_t qcap = (size_t)(n_bytes / (SHORT_MAX + 1)) + 4;
     CUDA_TRY(S.w_lq_start.ensure(qcap)); CUDA_TRY(S.w_lq_off.ensure(qcap));
     CUDA_TRY(S.w_lq_len.ensure(qcap)); CUDA_TRY(S.w_lq_ntok.ensure(qcap));
-    CUDA_TRY(S.w_lq_giant.ensure((size_t)(n_bytes / (GIANT_MIN + 1)) + 4));
+    size_t cls_cap[N_CLS], cls_total = 0;                          // per-class index lists, back to back
+    {
+        const size_t min_len[N_CLS] = {SHORT_MAX + 1, 33, 65, 129, 257, GIANT_MIN + 1};
+        for (int c = 0; c < N_CLS; c++) {
+            cls_cap[c] = (size_t)(n_bytes / min_len[c]) + 4;
+            cls_total += cls_cap[c];
+        }
+    }
+    CUDA_TRY(S.w_lq_cls.ensure(cls_total));
     CUDA_TRY(S.w_big_n.ensure((size_t)(n_bytes / (GIANT_MIN + 1)) + 4));
     CUDA_TRY(S.w_big_dst.ensure((size_t)(n_bytes / (GIANT_MIN + 1)) + 4)); CUDA_TRY(S.w_big_src.ensure((size_t)(n_bytes / (GIANT_MIN + 1)) + 4));
-    LongQ q{S.w_lq_start.p, S.w_lq_len.p, S.w_lq_off.p, S.w_lq_ntok.p, S.w_lq_giant.p};
+    LongQ q{S.w_lq_start.p, S.w_lq_len.p, S.w_lq_off.p, S.w_lq_ntok.p, {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr}};
+    { size_t o = 0; for (int c = 0; c < N_CLS; c++) { q.cls[c] = S.w_lq_cls.p + o; o += cls_cap[c]; } }
     uint32_t launches = 0;
 
     CUDA_TRY(cudaEventRecord(S.ev[0], st));
@@ -1563,6 +1433,11 @@ static int run_pipeline(b200bpe *h, Slot &S, const uint8_t *d_text, uint64_t n_b
         if (long_blocks > 148 * 8) long_blocks = 148 * 8;
     }
     CUDA_TRY(S.w_ltok.ensure((size_t)n_bytes + 4));
+    if (long_blocks) {
+        // 72 KiB of columns per block: 3 blocks per SM
+        mid_thread_kernel<<<148 * 3, MID_WARPS * 32, MID_SMEM_BYTES, st>>>(d_text, h->T, q, S.w_ltok.p, S.d_ctr);
+        launches++;
+    }
     if (long_blocks) {
         CUDA_TRY(S.w_idA.ensure(long_cap)); CUDA_TRY(S.w_rkA.ensure(long_cap));
         CUDA_TRY(S.w_idB.ensure(long_cap)); CUDA_TRY(S.w_rkB.ensure(long_cap));

@@ -285,4 +285,126 @@ B2_HD uint32_t merge_short_conv(const DevTables &T, ByteFn byte_at, int n, int n
     return mask;
 }
 
+// ------------------------------------------------------------------------------------------
+// Thread-per-piece merge for MID-size pieces (17 .. a few hundred bytes), warp-convergent like
+// merge_short_conv: every lane of `group` owns one piece and all lanes walk one instruction
+// stream (n_max = longest piece in the group).  The literal loop of `_byte_pair_merge`
+// (src/lib.rs:140-196): take the smallest rank (strict `<` => leftmost on ties), merge, re-rank
+// the two neighbouring pairs.
+// Parts live in two per-lane columns.  For the part that STARTS at byte j: id[j] = its token id,
+// rk[j] = rank of (part j, next part) or RANK_MAX.  A byte absorbed by the part to its left is DEAD:
+// id[j] = ID_DEAD and rk[j] is free, so the first and the last dead byte of every part carry a link
+// word MID_LINK | start << 12 | len of that part -- the neighbours of a part are found with two loads
+// instead of a walk over dead bytes.  Link words (and RANK_MAX) compare above every rank (< 2^30).
+// The minimum is kept two-level: gmin[g] / gpos[g] = smallest rank (leftmost) of the MID_G entries
+// of group g, so a round scans n / MID_G group minima and re-scans only the three groups whose
+// entries changed.  On return the tokens are the live id[j], j < n, left to right.
+// ------------------------------------------------------------------------------------------
+static const uint32_t ID_DEAD = 0xFFFFFFFFu;
+static const uint32_t MID_LINK = 0x80000000u;
+static const uint32_t MID_NONE = 0x40000000u;                  // "no mergeable pair": above every rank
+static const int MID_G = 8;
+
+template <class RkArr>
+B2_HD void mid_group_min(RkArr rk, int g, uint32_t &best, uint32_t &pos) {
+    best = MID_NONE; int bj = 0;
+#pragma unroll
+    for (int k = 0; k < MID_G; k++) {
+        const uint32_t r = rk[g * MID_G + k];
+        const bool lt = r < best;
+        best = lt ? r : best; bj = lt ? k : bj;
+    }
+    pos = (uint32_t)(g * MID_G + bj);
+}
+
+// id / rk need MID_G * ceil(n_max / MID_G) entries, gmin / gpos ceil(n_max / MID_G).
+// On entry rk[0 .. n_max) holds the piece's BYTES (the caller stages them; it needs them for the whole-piece
+// probe anyway), so that no pass here carries a dependent global-load chain.
+template <class IdArr, class RkArr, class GArr>
+B2_HD void merge_mid_conv(const DevTables &T, int n, int n_max, unsigned group, IdArr id, RkArr rk, GArr gmin, GArr gpos) {
+    const int ng = (n_max + MID_G - 1) / MID_G;
+    {
+        for (int j = n_max; j < ng * MID_G; j++) rk[j] = 0u;
+#pragma unroll 4
+        for (int j = 0; j < ng * MID_G; j++) {
+            const uint32_t b0 = rk[j], b1 = (j + 1 < ng * MID_G) ? rk[j + 1] : 0u;
+            uint32_t i0 = ID_DEAD, r0 = RANK_MAX;
+            if (j < n) {
+                i0 = B2_LDG_U32(T.byte_id + b0);
+                if (j + 1 < n) r0 = B2_LDG_U32(T.pair2 + (b0 << 8 | b1));
+            }
+            id[j] = i0; rk[j] = r0;
+        }
+        for (int g = 0; g < ng; g++) { uint32_t m, q; mid_group_min(rk, g, m, q); gmin[g] = m; gpos[g] = q; }
+    }
+    const int half = (ng + 1) >> 1;
+    for (;;) {
+        // two independent chains over the group minima (left half / right half); the right half wins
+        // only when strictly smaller => leftmost on ties
+        uint32_t bestA = MID_NONE, bestB = MID_NONE; int gA = 0, gB = 0;
+        for (int g = 0; g < half; g++) {
+            const uint32_t ra = gmin[g];
+            const uint32_t rb = (g + half < ng) ? gmin[g + half] : MID_NONE;
+            const bool la = ra < bestA, lb = rb < bestB;
+            bestA = la ? ra : bestA; gA = la ? g : gA;
+            bestB = lb ? rb : bestB; gB = lb ? g + half : gB;
+        }
+        const uint32_t best = bestB < bestA ? bestB : bestA;
+        const int bg = bestB < bestA ? gB : gA;
+        const bool act = best < MID_NONE;
+        if (!B2_ANY(group, act)) break;
+        int bj = 0, j2 = 1, j3 = n, jp = -1;
+        if (act) {
+            bj = (int)gpos[bg];
+            j2 = bj + 1; jp = bj - 1;
+            // right part of the merged pair (exists: rk[bj] is the rank of (bj, next)), the part after it
+            // and the left neighbour -- via the link words of the dead bytes at the parts' ends
+            if (id[j2] == ID_DEAD) j2 = bj + (int)(rk[j2] & 0xFFFu);
+            j3 = j2 + 1;
+            if (j3 < n && id[j3] == ID_DEAD) j3 = j2 + (int)(rk[j3] & 0xFFFu);
+            if (jp >= 0 && id[jp] == ID_DEAD) jp = (int)((rk[jp] >> 12) & 0xFFFu);
+        }
+        const bool need_r = act && j3 < n, need_l = act && jp >= 0;
+        uint32_t a1 = 0, b1 = 0, a2 = 0, b2 = 0;
+        if (need_r) { a1 = best; b1 = id[j3]; }
+        if (need_l) { a2 = id[jp]; b2 = best; }
+        if (act) {
+            const uint32_t link = MID_LINK | ((uint32_t)bj << 12) | (uint32_t)(j3 - bj);
+            id[bj] = best; id[j2] = ID_DEAD;
+            rk[j2] = link; rk[bj + 1] = link; rk[j3 - 1] = link;
+        }
+        // the two neighbour probes of every active lane, issued together
+        uint32_t s1 = pair_hash(a1, b1) & T.pair_mask, s2 = pair_hash(a2, b2) & T.pair_mask;
+        uint32_t r1 = RANK_MAX, r2 = RANK_MAX;
+        bool p1 = need_r, p2 = need_l;
+        while (B2_ANY(group, p1 || p2)) {
+            U4 e0 = {0, 0, 0, 0}, e1 = {0, 0, 0, 0}, f0 = {0, 0, 0, 0}, f1 = {0, 0, 0, 0};
+            if (p1) { e0 = B2_LDG_U4(T.pair_tab + 2 * s1); e1 = B2_LDG_U4(T.pair_tab + 2 * s1 + 1); }
+            if (p2) { f0 = B2_LDG_U4(T.pair_tab + 2 * s2); f1 = B2_LDG_U4(T.pair_tab + 2 * s2 + 1); }
+            if (p1) {
+                if (e0.x == a1 && e0.y == b1) { r1 = e0.z; p1 = false; }
+                else if (e1.x == a1 && e1.y == b1) { r1 = e1.z; p1 = false; }
+                else if (e1.x == 0xFFFFFFFFu) p1 = false;
+                else s1 = (s1 + 1) & T.pair_mask;
+            }
+            if (p2) {
+                if (f0.x == a2 && f0.y == b2) { r2 = f0.z; p2 = false; }
+                else if (f1.x == a2 && f1.y == b2) { r2 = f1.z; p2 = false; }
+                else if (f1.x == 0xFFFFFFFFu) p2 = false;
+                else s2 = (s2 + 1) & T.pair_mask;
+            }
+        }
+        if (act) {
+            rk[bj] = need_r ? r1 : RANK_MAX;
+            if (need_l) rk[jp] = r2;
+            // the groups whose ranks changed: bj's, j2's (its rank became a link) and jp's; duplicates
+            // just recompute the same values, so the three scans run back to back without votes
+            const int g1 = bj / MID_G, g2 = j2 / MID_G, g0 = need_l ? jp / MID_G : g1;
+            uint32_t m0, q0, m1, q1, m2, q2;
+            mid_group_min(rk, g0, m0, q0); mid_group_min(rk, g1, m1, q1); mid_group_min(rk, g2, m2, q2);
+            gmin[g0] = m0; gpos[g0] = q0; gmin[g1] = m1; gpos[g1] = q1; gmin[g2] = m2; gpos[g2] = q2;
+        }
+    }
+}
+
 }  // namespace b2bpe

@@ -52,6 +52,15 @@ extern "C" void *hc_tables_new(const uint8_t *tok_bytes, const uint64_t *tok_off
 }
 extern "C" void hc_tables_free(void *p) { delete (HcTables *)p; }
 extern "C" uint64_t hc_tables_pairs(void *p) { return ((HcTables *)p)->H.n_pairs; }
+// the two forms of the pair probe must agree: one at a time, two at a time
+extern "C" uint32_t hc_pair_lookup(void *p, uint32_t a, uint32_t b) {
+    DevTables T = ((HcTables *)p)->H.view();
+    const uint32_t r = pair_lookup(T, a, b);
+    uint32_t x, y; pair_lookup2(T, a, b, b, a, x, y);
+    if (r != x || y != pair_lookup(T, b, a)) return 0xDEADBEEFu;
+    return r;
+}
+extern "C" uint64_t hc_pair_buckets(void *p) { return (uint64_t)((HcTables *)p)->H.pair_mask + 1; }
 
 // the short path of the encode kernel for one piece of 1..16 bytes: whole-piece probe
 // (lib.rs:367-368) then merge_short; ids >= PSEUDO_BASE are reported as RANK_MAX.
@@ -71,6 +80,23 @@ extern "C" int hc_encode_short(void *p, const uint8_t *piece, uint32_t len, uint
     for (uint32_t m = mask; m;) { int j = __builtin_ffs(m) - 1; m &= m - 1; if (id[j] != id2[j]) return -2; }
     int k = 0;
     for (uint32_t m = mask; m;) { int j = __builtin_ffs(m) - 1; m &= m - 1; out[k++] = id[j] >= PSEUDO_BASE ? RANK_MAX : id[j]; }
+    return k;
+}
+
+// the thread-per-piece mid path (merge_mid_conv) for one piece of 2..cap bytes: whole-piece probe
+// then merge; n_max > n exercises the padding.  ids >= PSEUDO_BASE are reported as RANK_MAX.
+extern "C" int hc_encode_mid(void *p, const uint8_t *piece, uint32_t len, uint32_t cap, uint32_t *out) {
+    const HostTables &H = ((HcTables *)p)->H;
+    DevTables T = H.view();
+    if (len < 2 || len > cap) return -1;
+    uint32_t r = piece_lookup_long(T, long_hash_bytes(piece, len), len, [&](uint32_t i) { return piece[i]; });
+    if (len <= (uint32_t)SHORT_MAX) { uint64_t k0, k1; pack16(piece, len, k0, k1); r = piece_lookup16(T, k0, k1, len); }
+    if (r != RANK_MAX) { out[0] = r; return 1; }
+    std::vector<uint32_t> id(cap + 8, 0xABABABABu), rk(cap + 8, 0xABABABABu), gmin(cap / MID_G + 2, 7u), gpos(cap / MID_G + 2, 7u);
+    for (uint32_t j = 0; j < cap; j++) rk[j] = j < len ? piece[j] : 0u;          // the caller stages the bytes in rk
+    merge_mid_conv(T, (int)len, (int)cap, 1u, id.data(), rk.data(), gmin.data(), gpos.data());
+    int k = 0;
+    for (uint32_t j = 0; j < len; j++) if (id[j] != ID_DEAD) out[k++] = id[j] >= PSEUDO_BASE ? RANK_MAX : id[j];
     return k;
 }
 
