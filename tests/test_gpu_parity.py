@@ -193,3 +193,31 @@ def test_device_decode_batch_roundtrip_and_errors():
     assert e.decode_bytes_batch([]) == [] and e.decode_bytes_batch([[], []]) == [b"", b""]
     with pytest.raises(KeyError):
         e.decode_bytes_batch([[1, 2, 10 ** 7]])
+
+
+def test_mid_piece_length_classes_with_adversarial_vocabulary():
+    """Pieces of 17..300 bytes that are NOT tokens, on a tiny-alphabet vocabulary full of rank ties and
+    cascades, batched so that every length class of the one-piece-per-lane kernel (17-32 / 33-64 /
+    65-128 / 129-256 bytes, then the warp-per-piece path) sees full, ragged and single-lane warps."""
+    import random
+    import tiktoken_b200
+    from oracle import Oracle
+    rnd = random.Random(77)
+    for trial in range(3):
+        alpha = "abc"[: 2 + trial % 2] + "de"
+        ranks = {bytes([i]): i for i in range(256)}
+        toks = set()
+        for _ in range(60):
+            toks.add("".join(rnd.choice(alpha) for _ in range(rnd.choice([2, 2, 2, 3, 3, 4, 5, 7, 12, 20, 40]))).encode())
+        for t, r in zip(sorted(toks), rnd.sample(range(256, 1000), len(toks))):
+            ranks[t] = r
+        e = tiktoken_b200.Encoding("adv_mid", pat_str=vu.CL100K_PAT, mergeable_ranks=ranks, special_tokens={})
+        o = Oracle(ranks, {}, vu.CL100K_PAT)
+        lens = [16, 17, 18, 31, 32, 33, 34, 63, 64, 65, 66, 127, 128, 129, 130, 200, 255, 256, 257, 258, 300]
+        words = []
+        for n in lens:
+            for _ in range(rnd.choice([1, 5, 33, 70])):
+                words.append("".join(rnd.choice(alpha) for _ in range(n)))
+        rnd.shuffle(words)
+        docs = [" ".join(words), " ".join(words[::3]), words[0], ""]      # letters+ pieces split at the spaces
+        assert e.encode_ordinary_batch(docs) == [o.encode_ordinary(d) for d in docs]
