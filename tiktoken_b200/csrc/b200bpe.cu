@@ -108,22 +108,62 @@ __global__ void mark_docs_kernel(const unsigned long long *__restrict__ doc_off,
 
 // --------------------------------------------------------------------------------------------
 // kernel 1: pre-tokeniser.  One thread per 32-byte span = one word of the piece-start bitmask.
+// The positions the bit-parallel rules cannot decide locally go through the general rule function,
+// which is long and branchy: when a lane holds more than one of them, the warp pools its undecided
+// positions and deals them out one per lane, so that the function runs once per ~32 positions instead
+// of once per (busiest lane's) position with most lanes idle.
 // --------------------------------------------------------------------------------------------
+static const int PRETOK_WARPS = 8;
+
+// o200k's rule function is long (case / mark chains): one out-of-line copy serves both call sites; the
+// two shorter ones are cheaper inlined (measured both ways per pattern).
+__device__ __noinline__ bool slow_boundary_o200k(const TextAccess &t, long long pos) { return boundary_before<PAT_O200K>(t, pos); }
+
 template <int PAT>
-__global__ void __launch_bounds__(256) pretok_kernel(const uint8_t *__restrict__ text, long long n_bytes,
-                                                     const uint32_t *__restrict__ dbits, UcTables uc,
-                                                     uint32_t *__restrict__ pbits, uint32_t *__restrict__ psum,
-                                                     long long n_words) {
-    long long w = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    uint32_t word = 0;
-    if (w < n_words) {
-        TextAccess t{text, n_bytes, dbits, uc.stage1, uc.stage2, uc.ascii};
-        word = span_boundaries<PAT>(t, w);            // pretok_fast.cuh (+ pretok_rules.cuh for the rare cases)
-        pbits[w] = word;
+__device__ __forceinline__ bool slow_boundary(const TextAccess &t, long long pos) {
+    if (PAT == PAT_O200K) return slow_boundary_o200k(t, pos);
+    return boundary_before<PAT>(t, pos);
+}
+
+template <int PAT>
+__global__ void __launch_bounds__(PRETOK_WARPS * 32) pretok_kernel(const uint8_t *__restrict__ text, long long n_bytes,
+                                                                  const uint32_t *__restrict__ dbits, UcTables uc,
+                                                                  uint32_t *__restrict__ pbits, uint32_t *__restrict__ psum,
+                                                                  long long n_words) {
+    __shared__ uint16_t s_list[PRETOK_WARPS][1024];     // (owner lane << 5 | bit) of the pooled positions
+    __shared__ uint32_t s_res[PRETOK_WARPS][32];
+    const long long w = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const TextAccess t{text, n_bytes, dbits, uc.stage1, uc.stage2, uc.ascii};
+    uint64_t b = 0, slow = 0;
+    if (w < n_words) b = span_fast<PAT>(t, w, slow);
+    const uint32_t sm = (uint32_t)(slow >> 8);          // own positions only
+    const int cnt = __popc(sm);
+    const int mx = (int)__reduce_max_sync(0xFFFFFFFFu, (unsigned)cnt);
+    if (mx == 1) {
+        if (cnt && slow_boundary<PAT>(t, w * 32 + (__ffs(sm) - 1))) b |= (uint64_t)sm << 8;
+    } else if (mx > 1) {
+        int pre = cnt;                                  // inclusive scan over the lanes
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xFFFFFFFFu, pre, o); if (lane >= o) pre += v; }
+        const int total = __shfl_sync(0xFFFFFFFFu, pre, 31);
+        pre -= cnt;
+        s_res[warp][lane] = 0;
+        for (uint32_t mm = sm; mm; mm &= mm - 1) s_list[warp][pre++] = (uint16_t)((lane << 5) | (__ffs(mm) - 1));
+        __syncwarp();
+        const long long w0 = w - lane;
+        for (int i = lane; i < total; i += 32) {
+            const unsigned e = s_list[warp][i];
+            if (slow_boundary<PAT>(t, (w0 + (e >> 5)) * 32 + (e & 31))) atomicOr(&s_res[warp][e >> 5], 1u << (e & 31));
+        }
+        __syncwarp();
+        b |= (uint64_t)s_res[warp][lane] << 8;
     }
+    uint32_t word = 0;
+    if (w < n_words) { word = span_word(t, w, b); pbits[w] = word; }
     // summary bitmap: bit = "this word of pbits has a piece start" (lets find_long skip long runs 32x faster)
     const uint32_t nz = __ballot_sync(0xFFFFFFFFu, word != 0);
-    if ((threadIdx.x & 31) == 0 && (w >> 5) <= ((n_words - 1) >> 5)) psum[w >> 5] = nz;
+    if (lane == 0 && (w >> 5) <= ((n_words - 1) >> 5)) psum[w >> 5] = nz;
 }
 
 // single-piece mode (encode_single_piece): P = {0, n_bytes}

@@ -120,9 +120,13 @@ B2_HD void classify_window(const TextAccess &t, int64_t win0, int64_t w, WinMask
     }
 }
 
+// Fast part of a span: returns the boundary bits the local picture decides (window bit i = byte win0 + i,
+// own bytes are bits 8..39; document starts included) and, in `slow_out`, the own positions that
+// must be decided by the general rule function boundary_before<PAT>().
 template <int PAT>
-B2_HD uint32_t span_boundaries(const TextAccess &t, int64_t w, SpanStats *stats = nullptr) {
+B2_HD uint64_t span_fast(const TextAccess &t, int64_t w, uint64_t &slow_out, SpanStats *stats = nullptr) {
     const int64_t base = w * 32, win0 = base - 8;
+    slow_out = 0;
     if (base > t.n) return 0;
     WinMasks m;
     classify_window(t, win0, w, m);
@@ -215,14 +219,31 @@ B2_HD uint32_t span_boundaries(const TextAccess &t, int64_t w, SpanStats *stats 
     slow |= unk | (unk << 1) | (unk << 2) | (unk << 3) | (unk >> 1);
     slow &= own;
     b = (b & own & ~slow) | (m.D & OWN);
+    if (stats) { stats->positions += (unsigned long long)B2_POPCLL(own); stats->slow += (unsigned long long)B2_POPCLL(slow); }
+    slow_out = slow;
+    return b;
+}
+
+// window bits -> the span's word of the piece-start bitmask (+ the end-of-text sentinel)
+B2_HD uint32_t span_word(const TextAccess &t, int64_t w, uint64_t b) {
+    const int64_t base = w * 32;
+    if (base > t.n) return 0;
+    uint32_t word = (uint32_t)(b >> 8);
+    if (t.n >= base && t.n < base + 32) word |= 1u << (t.n - base);      // end sentinel
+    return word;
+}
+
+// one span, start to finish, by one thread (host checks, and the reference for the kernel's warp-cooperative form)
+template <int PAT>
+B2_HD uint32_t span_boundaries(const TextAccess &t, int64_t w, SpanStats *stats = nullptr) {
+    uint64_t slow;
+    uint64_t b = span_fast<PAT>(t, w, slow, stats);
+    const int64_t win0 = w * 32 - 8;
     for (uint64_t s = slow; s;) {
         const int j = B2_CTZLL(s); s &= s - 1;
         if (boundary_before<PAT>(t, win0 + j)) b |= 1ull << j;
     }
-    if (stats) { stats->positions += (unsigned long long)B2_POPCLL(own); stats->slow += (unsigned long long)B2_POPCLL(slow); }
-    uint32_t word = (uint32_t)(b >> 8);
-    if (t.n >= base && t.n < base + 32) word |= 1u << (t.n - base);      // end sentinel
-    return word;
+    return span_word(t, w, b);
 }
 
 }  // namespace b2bpe
