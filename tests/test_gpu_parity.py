@@ -135,6 +135,29 @@ def test_special_token_policy_and_slicing():
     assert e.encode_to_numpy(s, allowed_special="all").tolist() == o.encode(s, set(special))
 
 
+def test_many_special_occurrences_in_a_batch():
+    """Documents with thousands of allowed specials (adjacent, at both ends, overlapping look-alikes)
+    while other allowed specials never occur: every haystack boundary and every spliced id must match."""
+    import random
+    e, o, special = get("cl100k_base")
+    rnd = random.Random(9)
+    names = sorted(special)
+    words = ["alpha", " beta", "\n", " 42", "<|", "|>", "<|endoftext", " <|endoftext|", "x" * 40]
+    docs = []
+    for d in range(6):
+        parts = []
+        use = names if d % 2 else names[:1]
+        for _ in range(3000 if d < 2 else 200):
+            parts.append(rnd.choice(words) if rnd.random() < 0.7 else rnd.choice(use))
+        docs.append(rnd.choice(use) + "".join(parts) + rnd.choice(use) * 2)
+    docs += ["", names[0], names[0] * 3]
+    got = e.encode_batch(docs, allowed_special="all")
+    assert got == [o.encode(d, set(special)) for d in docs]
+    only = {names[0]}
+    got = e.encode_batch(docs, allowed_special=only, disallowed_special=())
+    assert got == [o.encode(d, only) for d in docs]
+
+
 def test_errors_and_misc_api():
     e, o, special = get("cl100k_base")
     with pytest.raises(KeyError):

@@ -6,9 +6,11 @@
 //
 //   mark_docs_kernel      doc_off[] -> doc-start bitmask D + first-doc-per-span index
 //   pretok_kernel<PAT>    UTF-8 bytes + D -> piece-start bitmask P   (bit-parallel regex rules)
-//   find_long_kernel      P -> queue of pieces longer than 16 bytes
-//   long_piece_kernel     17..4096 bytes: warp / half-warp per piece, one exact merge per round in
-//   giant_piece_kernel    shared memory; > 4096 bytes: a block per piece, round-synchronous merge
+//   find_long_kernel      P -> queue of pieces longer than 16 bytes + one work list per length class
+//   mid_thread_kernel     17..256 bytes: one piece per lane, 32 pieces per warp in one convergent
+//                         instruction stream, merge state in shared-memory columns
+//   long_piece_kernel     257..4096 bytes: a warp per piece;  giant_piece_kernel  > 4096 bytes: a block per
+//                         piece -- the round-synchronous exact merge in global scratch
 //   probe_kernel          one warp per 1 KiB sub-tile: whole-piece table probe of every short piece
 //                         (one 32 B sector each), one slot per piece, misses -> global queue
 //   miss_{hist,base,scatter}, miss_kernel   the ~5 % misses, sorted by length, one piece per lane,
@@ -1706,19 +1708,26 @@ extern "C" int b200bpe_encode_batch(b200bpe_t *h, const uint8_t *text, const uin
     std::vector<Cut> cuts; std::vector<uint64_t> doc_first_seg(n_docs + 1);
     std::vector<std::pair<std::string, uint32_t>> act;
     for (size_t i = 0; i < h->specials.size(); i++) if (allowed[i] && !h->specials[i].empty()) act.push_back({h->specials[i], h->special_rank[i]});
+    std::vector<uint64_t> nxt(act.size());                       // next occurrence of each allowed special in the document
     for (uint64_t d = 0; d < n_docs; d++) {
         doc_first_seg[d] = seg_off.size() - 1;
         uint64_t s = doc_off[d], e = doc_off[d + 1], pos = s;
+        // every special is searched once per stretch of text: its next occurrence is kept until the cursor
+        // passes it (a special that does not occur any more is never searched again in this document)
+        auto find_from = [&](size_t a, uint64_t from) -> uint64_t {
+            const std::string &sp = act[a].first;
+            if (from >= e || sp.size() > e - from) return e;
+            const void *f = memmem(text + from, (size_t)(e - from), sp.data(), sp.size());
+            return f ? (uint64_t)((const uint8_t *)f - text) : e;
+        };
+        for (size_t a = 0; a < act.size(); a++) nxt[a] = find_from(a, s);
         while (pos < e) {
             // leftmost allowed special at or after pos (longest on ties)
             uint64_t best_pos = e; size_t best = (size_t)-1;
             for (size_t a = 0; a < act.size(); a++) {
-                const std::string &sp = act[a].first;
-                if (sp.size() > e - pos) continue;
-                const void *f = memmem(text + pos, (size_t)(e - pos), sp.data(), sp.size());
-                if (!f) continue;
-                uint64_t fp = (uint64_t)((const uint8_t *)f - text);
-                if (fp < best_pos || (fp == best_pos && best != (size_t)-1 && sp.size() > act[best].first.size())) { best_pos = fp; best = a; }
+                if (nxt[a] < pos) nxt[a] = find_from(a, pos);
+                if (nxt[a] >= e) continue;
+                if (nxt[a] < best_pos || (nxt[a] == best_pos && act[a].first.size() > act[best].first.size())) { best_pos = nxt[a]; best = a; }
             }
             ctext.insert(ctext.end(), text + pos, text + best_pos);
             seg_off.push_back(ctext.size());
