@@ -210,7 +210,7 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     import tiktoken_b200
-    from tiktoken_b200.sharding import gather_counts
+    from tiktoken_b200.sharding import CountExchange, gather_counts
 
     enc = tiktoken_b200.Encoding(enc_name + "_bench", pat_str=pat, mergeable_ranks=ranks, special_tokens=special,
                                  device=local_rank)
@@ -264,13 +264,16 @@ def main():
     stage = {"pretok_ms": [], "encode_ms": [], "probe_ms": [], "gather_ms": [], "long_ms": [], "mark_docs_ms": [], "device_total_ms": []}
     launches = 0
     ev0.record(stream)
+    xchg = CountExchange(rank, world, device="cuda")
     for _ in range(args.steps):
         n_tok = step_device()
-        counts, _, _ = gather_counts(n_tok, n_docs, rank, world, device="cuda")   # NCCL all-gather of counts
+        xchg.post(n_tok, n_docs)           # NCCL all-gather of (tokens, docs), next to the following step's kernels
         tm = core.last_timings()
         for key in stage:
             stage[key].append(tm[key])
         launches += tm["launches"]
+    placements = xchg.drain()              # every exchange completes inside the timed region
+    counts = placements[-1][0]
     ev1.record(stream)
     barrier()
     clocks = sampler.stop()

@@ -32,10 +32,28 @@ def _worker(rank, world, port, q):
     o = Oracle(ranks, special, pat)
     text, off = corpus.config4(n_docs=4000, seed=77)
     res = encode_sharded(lambda t, d: o.encode_ordinary_batch_np(t, d, 1), text, off, rank, world)
+    # the asynchronous form of the same exchange: three batches posted back to back, collected in order
+    from tiktoken_b200.sharding import CountExchange, gather_counts
+    x = CountExchange(rank, world)
+    for k in range(3):
+        x.post(100 * (rank + 1) + k, 7 + rank)
+    async_ok = True
+    for k, (counts, tbase, dbase) in enumerate(x.drain()):
+        exp = gather_counts(100 * (rank + 1) + k, 7 + rank, rank, world)
+        async_ok &= np.array_equal(counts, exp[0]) and (tbase, dbase) == (exp[1], exp[2])
+    assert async_ok
     q.put((rank, res["doc_range"], res["token_base"], res["doc_base"], res["total_tokens"],
            res["tokens"].tobytes(), res["tok_off"].tobytes()))
     dist.barrier()
     dist.destroy_process_group()
+
+
+def test_count_exchange_single_process():
+    from tiktoken_b200.sharding import CountExchange
+    x = CountExchange(0, 1)
+    x.post(5, 2); x.post(9, 3)
+    (c0, t0, d0), (c1, t1, d1) = x.drain()
+    assert c0.tolist() == [[5, 2]] and c1.tolist() == [[9, 3]] and (t0, d0, t1, d1) == (0, 0, 0, 0)
 
 
 def test_world2_gloo_matches_single_process():

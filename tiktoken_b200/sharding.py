@@ -57,3 +57,59 @@ def encode_sharded(encode_packed, text: np.ndarray, doc_off: np.ndarray, rank: i
     counts, token_base, doc_base = gather_counts(int(len(tokens)), hi - lo, rank, world, device)
     return {"doc_range": (lo, hi), "tokens": tokens, "tok_off": tok_off, "token_base": token_base,
             "doc_base": doc_base, "counts": counts, "total_tokens": int(counts[:, 0].sum())}
+
+
+class CountExchange:
+    """The same all-gather as `gather_counts`, posted asynchronously on preallocated buffers so that a
+    stream of batches does not stop for it: `post()` after batch k, `wait()` (any time later) returns
+    (counts[world,2], token_base, doc_base) of that batch.  With an NCCL group the exchange runs on the
+    communicator's stream next to the kernels of batch k+1; the placement is only needed when the shard
+    is written out."""
+
+    def __init__(self, rank: int, world: int, device=None):
+        import torch
+        import torch.distributed as dist
+        self.rank, self.world = rank, world
+        self.active = world > 1 and dist.is_initialized()
+        self._pending = []
+        if self.active:
+            self._dev = device or "cpu"
+            self._pool = []                                  # reusable (host, mine, gathered) buffer sets
+
+    def _buffers(self):
+        import torch
+        if self._pool:
+            return self._pool.pop()
+        pin = self._dev != "cpu" and torch.cuda.is_available()
+        host = torch.zeros(2, dtype=torch.int64, pin_memory=pin)
+        mine = torch.zeros(2, dtype=torch.int64, device=self._dev)
+        gathered = [torch.zeros(2, dtype=torch.int64, device=self._dev) for _ in range(self.world)]
+        return host, mine, gathered
+
+    def post(self, n_tokens: int, n_docs: int) -> None:
+        if not self.active:
+            self._pending.append((None, None, (int(n_tokens), int(n_docs))))
+            return
+        import torch.distributed as dist
+        host, mine, gathered = self._buffers()
+        host[0] = int(n_tokens); host[1] = int(n_docs)
+        mine.copy_(host, non_blocking=True)
+        work = dist.all_gather(gathered, mine, async_op=True)
+        self._pending.append((work, (host, mine, gathered), None))
+
+    def wait(self):
+        import torch
+        work, bufs, local = self._pending.pop(0)
+        if work is None:
+            counts = np.asarray([local], dtype=np.int64)
+            return counts, 0, 0
+        work.wait()
+        counts = torch.stack(bufs[2]).cpu().numpy()
+        self._pool.append(bufs)
+        return counts, int(counts[:self.rank, 0].sum()), int(counts[:self.rank, 1].sum())
+
+    def drain(self):
+        out = []
+        while self._pending:
+            out.append(self.wait())
+        return out
