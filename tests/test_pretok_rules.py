@@ -156,3 +156,35 @@ def test_fast_path_documents_are_separate_haystacks(hostcheck):
     assert got.tolist() == [1, 1, 1, 0]
     got, _, _ = fast_starts(hostcheck, 2, [b"", b"", b"x", b""])
     assert got.tolist() == [1]
+
+
+@pytest.mark.parametrize("name", ["cl100k", "o200k"])
+def test_fast_path_digit_run_behind_a_scalar_cut_by_the_window(hostcheck, name):
+    """Regression (found by tools/fuzz_cpu.py): a non-ASCII digit whose lead byte lies before a span's
+    48-byte window left 'unknown' continuation bytes that were taken for a non-digit, so an ASCII digit
+    run right after it got a wrong run start.  Slide digit runs behind 2-, 3- and 4-byte digits (and
+    non-digits) over every alignment."""
+    pid, pat = PATS[name]
+    o = Oracle(BYTES, {}, pat)
+    heads = ["\u00b2", "\u0660", "\u2160", "\uff12", "\U0001d7d8", "\u4e2d", "\u00e9", "\U0001f600"]
+    docs = []
+    for pad in range(0, 40):
+        for head in heads:
+            for reps in (1, 2):
+                for nd in (1, 3, 6, 7, 8, 9, 10):
+                    docs.append(("a" * pad + head * reps + "2" * nd + " x").encode())
+    got, off, _ = fast_starts(hostcheck, pid, docs)
+    for i, d in enumerate(docs):
+        assert np.array_equal(got[int(off[i]):int(off[i + 1])], expected_starts(o, d)), d
+
+
+def test_fuzz_harness_short_run():
+    """tools/fuzz_cpu.py (random multi-document batches through the kernel's pre-tokeniser code, random
+    adversarial vocabularies through its merge code, both against the oracle) for a few seconds."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "tools", "fuzz_cpu.py"), "8", "4242"],
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "all equal" in r.stdout

@@ -142,6 +142,7 @@ B2_HD uint64_t span_fast(const TextAccess &t, int64_t w, uint64_t &slow_out, Spa
     const uint64_t pL = L << 1, pN = m.N << 1, pSP = m.SP << 1, pNL = m.NL << 1, pWSnn = WSnn << 1;
     const uint64_t pWSany = WSany << 1, pAPOS = m.APOS << 1, pHi = m.hi << 1;
     uint64_t b = 0, slow = 0;
+    const uint64_t unk0 = m.valid & ~(m.LU | m.LL | m.LB | m.M | m.N | m.SP | m.WS | m.NL | m.APOS | m.SLASH | m.O);
     if (PAT == PAT_R50K) {
         const uint64_t X = m.O | m.APOS | m.SLASH | m.M;
         const uint64_t pX = X << 1;
@@ -164,7 +165,9 @@ B2_HD uint64_t span_fast(const TextAccess &t, int64_t w, uint64_t &slow_out, Spa
             // multiple of 3.  Runs of ASCII digits that start within the 8-byte look-back are counted with
             // shifts; longer or non-ASCII runs go the slow way.
             const uint64_t A = m.NA;
-            const uint64_t rs = A & ~(m.N << 1);                       // an ASCII digit that starts its run
+            // an ASCII digit that starts its run.  A byte whose class is unknown here (continuation bytes of a
+            // scalar that begins before the window) may belong to a non-ASCII digit: no known run start after it
+            const uint64_t rs = A & ~((m.N | unk0) << 1);
             const uint64_t c1 = A << 1, c2 = c1 & (A << 2), c3 = c2 & (A << 3), c4 = c3 & (A << 4);
             const uint64_t c5 = c4 & (A << 5), c6 = c5 & (A << 6), c7 = c6 & (A << 7);
             const uint64_t k1 = rs << 1, k2 = c1 & (rs << 2), k3 = c2 & (rs << 3), k4 = c3 & (rs << 4);
@@ -196,7 +199,9 @@ B2_HD uint64_t span_fast(const TextAccess &t, int64_t w, uint64_t &slow_out, Spa
             // multiple of 3.  Runs of ASCII digits that start within the 8-byte look-back are counted with
             // shifts; longer or non-ASCII runs go the slow way.
             const uint64_t A = m.NA;
-            const uint64_t rs = A & ~(m.N << 1);                       // an ASCII digit that starts its run
+            // an ASCII digit that starts its run.  A byte whose class is unknown here (continuation bytes of a
+            // scalar that begins before the window) may belong to a non-ASCII digit: no known run start after it
+            const uint64_t rs = A & ~((m.N | unk0) << 1);
             const uint64_t c1 = A << 1, c2 = c1 & (A << 2), c3 = c2 & (A << 3), c4 = c3 & (A << 4);
             const uint64_t c5 = c4 & (A << 5), c6 = c5 & (A << 6), c7 = c6 & (A << 7);
             const uint64_t k1 = rs << 1, k2 = c1 & (rs << 2), k3 = c2 & (rs << 3), k4 = c3 & (rs << 4);
@@ -214,8 +219,7 @@ B2_HD uint64_t span_fast(const TextAccess &t, int64_t w, uint64_t &slow_out, Spa
         slow |= WSnn & (pNL | (m.hi & pWSany));
     }
     // anything that touches an undecoded (truncated / unknown) non-ASCII byte goes the slow way
-    const uint64_t known = m.LU | m.LL | m.LB | m.M | m.N | m.SP | m.WS | m.NL | m.APOS | m.SLASH | m.O;
-    const uint64_t unk = m.valid & ~known;
+    const uint64_t unk = unk0;
     slow |= unk | (unk << 1) | (unk << 2) | (unk << 3) | (unk >> 1);
     slow &= own;
     b = (b & own & ~slow) | (m.D & OWN);
