@@ -35,7 +35,23 @@ POOL = list("aAbzZ sStTdDmMlLvVeErR0123456789 \t\n\r\x0b\x0c!?.,;:'\"/-_()[]{}<>
     "ั"]
 
 
+# fragments that exercise the alternatives as wholes: contractions in every case (incl. U+017F / U+212A case
+# folds), whitespace / newline mixtures, digit groups, punctuation runs with trailing newlines and slashes
+FRAGS = ["'s", "'S", "'t", "'re", "'VE", "'m", "'ll", "'LL", "'d", "'\u017f", "'\u212a", "'x", "''", "'", " '",
+         " ", "  ", "   ", "\t", " \t ", "\n", "\r\n", "\n\n", " \n", "\n ", " \n ", "\r", "\u3000", "\u00a0\n", "\x0b",
+         "1", "12", "123", "1234", "12345678", "\uff11\uff12", "\u0663", "1\u0663" "2",
+         "!", "!!", "...", "/", "//", "!/", "!\n", "!\n\n/", "-\r\n", "(", ")", "_", "\u3001", "\u300c", "\u2019",
+         "word", "Word", "WORD", "wOrD", "camelCase", "HTTPServer", "\u00e9t\u00e9", "\u00c9T\u00c9", "\u4e2d\u6587", "\u0e01\u0e31",
+         "a\u0301", "\u0301", "\u0301\u0301", "A\u0301b", "\u01c5x", "x\u01c5", "\u02b0", "\U0001f600", "\U0001f600\u200d\U0001f3fb"]
+
+
+def rnd_doc_frags(rnd):
+    return "".join(rnd.choice(FRAGS) for _ in range(rnd.choice([0, 1, 2, 3, 5, 8, 13, 30, 60])))
+
+
 def rnd_doc(rnd):
+    if rnd.random() < 0.4:
+        return rnd_doc_frags(rnd)
     n = rnd.choice([0, 1, 2, 3, 5, 8, 13, 21, 40, 80, 200])
     if rnd.random() < 0.5:
         return "".join(rnd.choice(POOL) for _ in range(n))
