@@ -188,3 +188,25 @@ def test_fuzz_harness_short_run():
                        capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "all equal" in r.stdout
+
+
+@pytest.mark.timeout(120)
+def test_malformed_utf8_terminates(hostcheck):
+    """The packed / device entry points take raw bytes.  Malformed UTF-8 has no reference answer, but the
+    rule code must still terminate and stay in bounds (a forward walk in the o200k chain automaton used to
+    step over its target on such input and never end)."""
+    rnd = random.Random(3)
+    for it in range(400):
+        mode = it % 3
+        n = rnd.choice([1, 5, 33, 100, 1000])
+        if mode == 0:
+            blob = bytes(rnd.randrange(256) for _ in range(n))
+        elif mode == 1:
+            blob = bytes(rnd.choice([0x80, 0xBF, 0xE0, 0xF0, 0xC2, 0x41, 0x20, 0x0A, 0xFF, 0xF8, 0x27]) for _ in range(n))
+        else:
+            blob = bytes([rnd.choice([0x80, 0xE3, 0xF0])]) * n
+        cuts = sorted(rnd.randrange(n + 1) for _ in range(rnd.randint(0, 3)))
+        docs = [blob[a:b] for a, b in zip([0] + cuts, cuts + [n])]
+        for pid in range(3):
+            got, _, _ = fast_starts(hostcheck, pid, docs)
+            assert len(got) == n

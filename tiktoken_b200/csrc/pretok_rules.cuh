@@ -249,6 +249,9 @@ B2_HDN XmState o200k_xm_state(const T &t, int64_t q) {
     const bool joined_ws = (ctx == C_SP || ctx == C_WS);    // any free non-CR/LF ws prefixes a word
     XmState out = { XS_XRUN, false };
     for (int64_t e = r;; e = t.next(e)) {
+        // On well-formed UTF-8 the forward walk lands exactly on q.  On malformed input next() can step over
+        // it: stop there (the answer for such bytes is unspecified, the walk must still end).
+        if (e < 0 || e > q) { out.st = st < 0 ? XS_XRUN : st; break; }
         const int ce = t.cls(e);
         bool start = false;
         if (ce == C_NL) {
