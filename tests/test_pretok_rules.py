@@ -210,3 +210,57 @@ def test_malformed_utf8_terminates(hostcheck):
         for pid in range(3):
             got, _, _ = fast_starts(hostcheck, pid, docs)
             assert len(got) == n
+
+
+def test_next_round_o200k_prefix_rule_is_exact():
+    """pretok_fast.cuh carries one rule that is NOT in the shipped kernels yet (B2_O200K_FAST_PREFIX, off by
+    default until it has been measured and validated on the GPU): a letter after a punctuation scalar decided
+    bit-parallel as boundary(p) = !boundary(x).  Build the host check WITH it and hold it to the same standard
+    as the shipped rules: exhaustive strings, the real engine's random Unicode splits, a mixed-script corpus,
+    and a short fuzz run."""
+    import ctypes as C
+    import subprocess
+    import sys
+    from conftest import ROOT
+    csrc = os.path.join(ROOT, "tiktoken_b200", "csrc")
+    so = os.path.join(csrc, "libb200bpe_hostcheck_next.so")
+    subprocess.check_call(["g++", "-O2", "-fPIC", "-shared", "-std=c++17", "-DB2_O200K_FAST_PREFIX=1", "-o", so,
+                           os.path.join(csrc, "hostcheck.cpp")])
+    H = C.CDLL(so)
+    H.hc_piece_starts_fast.argtypes = [C.c_int, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
+    pid, pat = PATS["o200k"]
+    o = Oracle(BYTES, {}, pat)
+    spec = json.load(open(os.path.join(G, "splits_exhaustive.json")))["o200k"]
+    for l in range(1, spec["max_len"]):
+        docs = ["".join(t).encode() for t in itertools.product(spec["alphabet"], repeat=l)]
+        got, off, _ = fast_starts(H, pid, docs)
+        for i, d in enumerate(docs):
+            assert np.array_equal(got[int(off[i]):int(off[i + 1])], expected_starts(o, d)), d
+    # punctuation of every UTF-8 length in front of letters of every kind, at every alignment
+    xs = ["(", "«", "、", "\U0001f600", "'", "/", "́"]
+    befores = ["a", "1", " ", "\t", "\n", "(", "'", "、", "", "́", "/", "中"]
+    letters = ["a", "A", "中", "é", "ǅ"]
+    docs = []
+    for pad in range(0, 34):
+        for bf in befores:
+            for x in xs:
+                for le in letters:
+                    docs.append(("z" * pad + bf + x + le + "b c").encode())
+    got, off, _ = fast_starts(H, pid, docs)
+    for i, d in enumerate(docs):
+        assert np.array_equal(got[int(off[i]):int(off[i + 1])], expected_starts(o, d)), d
+    cases = json.load(open(os.path.join(G, "splits_random.json")))["o200k"]
+    docs = [bytes.fromhex(t) for t, _ in cases]
+    got, off, _ = fast_starts(H, pid, docs)
+    for i, d in enumerate(docs):
+        assert np.array_equal(got[int(off[i]):int(off[i + 1])], expected_starts(o, d)), d
+    from tools import corpus
+    text = corpus.generate(corpus.MIXED, 99, 1 << 20)
+    _, doff = corpus.docs_fixed(text, 30000, at_space=False)
+    cdocs = [text[int(doff[i]):int(doff[i + 1])].tobytes() for i in range(len(doff) - 1)]
+    got, off, st_new = fast_starts(H, pid, cdocs)
+    for i, d in enumerate(cdocs):
+        assert np.array_equal(got[int(off[i]):int(off[i + 1])], expected_starts(o, d))
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "fuzz_cpu.py"), "6", "777"], capture_output=True,
+                       text=True, timeout=300, env=dict(os.environ, B200BPE_HOSTCHECK=so))
+    assert r.returncode == 0 and "all equal" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]

@@ -16,6 +16,12 @@ namespace b2bpe {
 
 struct SpanStats { unsigned long long positions, slow; };
 
+// Next-round rule, verified on the CPU (tests/test_pretok_rules.py builds the host check with it) but not yet
+// measured / validated on the GPU: the shipped kernels are compiled with it OFF.
+#ifndef B2_O200K_FAST_PREFIX
+#define B2_O200K_FAST_PREFIX 0
+#endif
+
 #if defined(__CUDA_ARCH__)
 #define B2_CTZLL(x) (__ffsll((long long)(x)) - 1)
 #define B2_POPCLL(x) __popcll(x)
@@ -187,10 +193,35 @@ B2_HD uint64_t span_fast(const TextAccess &t, int64_t w, uint64_t &slow_out, Spa
         const uint64_t Xo = m.O | m.APOS | m.SLASH;
         const uint64_t pXo = Xo << 1, pM = m.M << 1, pLB = m.LB << 1, pLL = m.LL << 1, pLU = m.LU << 1;
         const uint64_t low = m.LL | m.LB;                           // extends any word
+#if B2_O200K_FAST_PREFIX
+        b |= low & (pN | pNL);
+        b |= m.LU & (pLL | pN | pNL);
+        // A letter right after an "other" scalar x (punctuation, symbol; not apostrophe / slash / mark): x is either
+        // the optional one-scalar prefix of the word (a piece starts AT x) or the end of a punctuation run (a piece
+        // started before x), so  boundary(p) = !boundary(x),  and boundary(x) follows from the scalar before x:
+        // letter / digit / non-space whitespace / CR-LF / document start => a piece starts at x;  space, other or
+        // apostrophe => x continues (or is joined to) what precedes it.  x may be 1..4 bytes long.
+        {
+            const uint64_t pO = m.O << 1, leadNA = m.hi & ~m.cont, c1 = m.cont << 1, c2 = m.cont << 2, c3 = m.cont << 3;
+            const uint64_t len1 = pO & ~(m.hi << 1), len2 = pO & c1 & (leadNA << 2), len3 = pO & c1 & c2 & (leadNA << 3);
+            const uint64_t len4 = pO & c1 & c2 & c3 & (leadNA << 4);
+            const uint64_t Q1 = L | m.N | m.WS | m.NL, Q0 = m.SP | m.O | m.APOS;
+            const uint64_t atD = (len1 & (m.D << 1)) | (len2 & (m.D << 2)) | (len3 & (m.D << 3)) | (len4 & (m.D << 4));
+            const uint64_t x1 = (len1 & (Q1 << 2)) | (len2 & (Q1 << 3)) | (len3 & (Q1 << 4)) | (len4 & (Q1 << 5)) | atD;
+            const uint64_t x0 = ((len1 & (Q0 << 2)) | (len2 & (Q0 << 3)) | (len3 & (Q0 << 4)) | (len4 & (Q0 << 5))) & ~atD;
+            const uint64_t letter_after_o = (low | m.LU) & pO;
+            b |= letter_after_o & x0;
+            slow |= letter_after_o & ~(x0 | x1);
+            const uint64_t pXrest = (m.APOS | m.SLASH) << 1;
+            slow |= low & (pXrest | pM | (pL & aposNear));
+            slow |= m.LU & (pLB | pM | pXrest | ((pLL | pLU) & aposNear));
+        }
+#else
         b |= low & (pN | pNL);
         slow |= low & (pXo | pM | (pL & aposNear));
         b |= m.LU & (pLL | pN | pNL);
         slow |= m.LU & (pLB | pM | pXo | ((pLL | pLU) & aposNear));
+#endif
         slow |= m.M | m.APOS | m.SLASH;
         b |= m.O & (pL | pN | ((m.WS | m.NL) << 1));
         slow |= m.O & (pM | (m.SLASH << 1));

@@ -18,7 +18,7 @@ import vocab_util as vu  # noqa: E402
 from oracle import Oracle  # noqa: E402
 from oracle.oracle import _flatten  # noqa: E402
 
-H = C.CDLL(os.path.join(ROOT, "tiktoken_b200", "csrc", "libb200bpe_hostcheck.so"))
+H = C.CDLL(os.environ.get("B200BPE_HOSTCHECK") or os.path.join(ROOT, "tiktoken_b200", "csrc", "libb200bpe_hostcheck.so"))
 H.hc_piece_starts_fast.argtypes = [C.c_int, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
 H.hc_tables_new.restype = C.c_void_p
 H.hc_tables_new.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]
