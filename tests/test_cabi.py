@@ -78,3 +78,54 @@ def test_pack_helper_matches_python_marshalling():
     toff = np.asarray([0, 0, 3, 3, 10], np.uint64)
     got = T._b200pack.unpack(toks.ctypes.data, toff.ctypes.data, 4)
     assert got == [[], toks[:3].tolist(), [], toks[3:].tolist()]
+
+
+def test_packed_disallowed_special_scan_matches_the_regex_check():
+    """_b200pack.find_first (the batch form of the disallowed-special check, tiktoken/core.py:120-124) against
+    the per-document regex search it replaces; matches never straddle documents; the host class raises the
+    reference's ValueError."""
+    import random
+    import regex
+    import __graft_entry__  # noqa: F401  (sys.path)
+    from tiktoken_b200 import _tiktoken as T, core
+    assert T._b200pack is not None
+    sp = ["<|endoftext|>", "<|fim_prefix|>", "<|fim_middle|>", "<|fim_suffix|>", "<|endofprompt|>"]
+    rx = regex.compile("|".join(regex.escape(s) for s in sp))
+    rnd = random.Random(1)
+    frags = ["hello ", "<|", "|>", "<|endoftext", "<|endoftext|>", "<|fim_prefix|>", "<", "é<|endofprompt|>", "x" * 50, "\n"]
+    for _ in range(1500):
+        docs = ["".join(rnd.choice(frags) for _ in range(rnd.randint(0, 12))) for _ in range(rnd.randint(1, 6))]
+        blob, offs = T._b200pack.pack(docs)
+        got = T._b200pack.find_first(blob, offs, [s.encode() for s in sp])
+        exp = None
+        for d, t in enumerate(docs):
+            m = rx.search(t)
+            if m:
+                exp = (d, sp.index(m.group()))
+                break
+        assert (got is None) == (exp is None) and (got is None or (got[0], got[1]) == exp), docs
+        # needles with different first bytes take the memmem path
+        got2 = T._b200pack.find_first(blob, offs, [b"hello", b"<|endoftext|>", b"x" * 50])
+        exp2 = None
+        for d, t in enumerate(docs):
+            hits = [(t.encode().find(n), -len(n), i) for i, n in enumerate([b"hello", b"<|endoftext|>", b"x" * 50])
+                    if t.encode().find(n) >= 0]
+            if hits:
+                exp2 = (d, min(hits)[2])
+                break
+        assert (got2 is None) == (exp2 is None) and (got2 is None or (got2[0], got2[1]) == exp2), docs
+    blob, offs = T._b200pack.pack(["a<|endof", "text|>b"])
+    assert T._b200pack.find_first(blob, offs, [b"<|endoftext|>"]) is None
+
+    class HostOnly(core.Encoding):                  # the check itself needs no engine
+        def __init__(self):
+            pass
+    e = HostOnly()
+    docs = ["hello", "a <|endoftext|> b", ""]
+    t, off = T.CoreBPE._pack(docs)
+    with pytest.raises(ValueError, match="disallowed special token '<\\|endoftext\\|>'"):
+        e._check_disallowed_packed(docs, t, off, frozenset({"<|endoftext|>", "<|x|>"}))
+    e._check_disallowed_packed(docs, t, off, frozenset({"<|x|>"}))
+    e._check_disallowed_packed(docs, t, off, frozenset())
+    t, off = T.CoreBPE._pack([])
+    e._check_disallowed_packed([], t, off, frozenset({"<|x|>"}))
