@@ -98,6 +98,11 @@ static PyObject *find_first(PyObject *self, PyObject *args) {
         const uint8_t *text = (const uint8_t *)blob.buf;
         const uint64_t *off = (const uint64_t *)offs.buf;
         const Py_ssize_t n_docs = offs.len / 8 - 1;
+        for (Py_ssize_t d = 0; d < n_docs; d++)
+            if (off[d] > off[d + 1] || off[d + 1] > (uint64_t)blob.len) {
+                PyErr_SetString(PyExc_ValueError, "offsets must be non-decreasing and end inside the blob");
+                goto done;
+            }
         Py_ssize_t hit_doc = -1, hit_a = -1; uint64_t hit_pos = 0;
         Py_BEGIN_ALLOW_THREADS
         for (Py_ssize_t d = 0; d < n_docs && hit_doc < 0 && nn > 0; d++) {
