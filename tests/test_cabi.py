@@ -129,3 +129,53 @@ def test_packed_disallowed_special_scan_matches_the_regex_check():
     e._check_disallowed_packed(docs, t, off, frozenset())
     t, off = T.CoreBPE._pack([])
     e._check_disallowed_packed([], t, off, frozenset({"<|x|>"}))
+
+
+def test_host_shim_construction_paths_with_a_stub_library(monkeypatch):
+    """The two ways to build an engine (dict, as tiktoken/core.py:57 does, and flattened arrays parsed in C from a
+    `.tiktoken` file) hand the SAME arrays to b200bpe_create, and the table-read methods / pickling state work
+    from either.  The native library is stubbed (no GPU here); everything up to and after the call is real."""
+    import base64
+    import gzip
+    import pickle
+    import __graft_entry__  # noqa: F401  (sys.path)
+    from tiktoken_b200 import _tiktoken as T, core
+
+    captured = []
+
+    class Stub:
+        def b200bpe_create(self, tb, to, tr, n, sb, so, sr, ns, pat, dev, out):
+            import ctypes as C2
+            blob = bytes((C2.c_uint8 * 1).from_address(tb.value)) if n == 0 else None
+            off = np.ctypeslib.as_array(C2.cast(to, C2.POINTER(C2.c_uint64)), shape=(n + 1,)).copy()
+            rk = np.ctypeslib.as_array(C2.cast(tr, C2.POINTER(C2.c_uint32)), shape=(max(n, 1),))[:n].copy()
+            data = np.ctypeslib.as_array(C2.cast(tb, C2.POINTER(C2.c_uint8)), shape=(max(int(off[-1]), 1),))[:int(off[-1])].copy()
+            captured.append((data.tobytes(), off.tolist(), rk.tolist(), n, ns, pat, blob))
+            return 0
+
+        def b200bpe_destroy(self, h):
+            pass
+
+    monkeypatch.setattr(T._lib, "lib", lambda: Stub())
+    path = os.path.join(ROOT, "tests", "golden", "vocab", "r50k_like.tiktoken.gz")
+    data = gzip.open(path).read()
+    ranks = {base64.b64decode(t): int(r) for t, r in (ln.split() for ln in data.splitlines() if ln)}
+    special = {"<|endoftext|>": 50256}
+    e1 = core.Encoding("by_dict", pat_str=vu.R50K_PAT, mergeable_ranks=ranks, special_tokens=special)
+    e2 = core.Encoding.from_tiktoken_file("by_file", path, pat_str=vu.R50K_PAT, special_tokens=special,
+                                          explicit_n_vocab=50257)
+    e3 = core.Encoding.from_tiktoken_file("by_bytes", data, pat_str=vu.R50K_PAT, special_tokens=special)
+    assert captured[0][:6] == captured[1][:6] == captured[2][:6]
+    for e in (e1, e2, e3):
+        assert e.n_vocab == 50257 and e.max_token_value == 50256
+        assert e._core_bpe.encode_single_token(b"a") == ranks[b"a"]
+        assert e._core_bpe.encode_single_token(b"<|endoftext|>") == 50256
+        assert e._core_bpe.decode_single_token_bytes(ranks[b"th"] if b"th" in ranks else 97) in ranks
+        assert e._core_bpe.token_byte_values() == sorted(ranks)
+        assert e._mergeable_ranks == ranks
+        state = e.__getstate__()
+        assert state["mergeable_ranks"] == ranks and state["pat_str"] == vu.R50K_PAT
+        e4 = pickle.loads(pickle.dumps(e))                      # by value: rebuilds through __init__
+        assert e4._mergeable_ranks == ranks and e4.name == e.name
+    with pytest.raises(ValueError):
+        T.CoreBPE.from_flat(np.zeros(3, np.uint8), np.asarray([0, 5], np.uint64), np.asarray([1], np.uint32), {}, vu.R50K_PAT)

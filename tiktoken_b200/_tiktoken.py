@@ -69,11 +69,35 @@ class TokenBuffer:
 class CoreBPE:
     def __init__(self, mergeable_ranks: dict[bytes, int], special_tokens: dict[str, int], pat_str: str,
                  device: int | None = None):
-        L = _lib.lib()
-        self._L = L
         toks = list(mergeable_ranks.keys())
         blob, off = _flatten_bytes(toks)
         ranks = np.fromiter((mergeable_ranks[t] for t in toks), dtype=np.uint32, count=len(toks))
+        self._create(blob, off, ranks, special_tokens, pat_str, device)
+        self._encoder_dict = mergeable_ranks
+
+    @classmethod
+    def from_flat(cls, tok_bytes: np.ndarray, tok_off: np.ndarray, tok_rank: np.ndarray, special_tokens: dict[str, int],
+                  pat_str: str, device: int | None = None) -> "CoreBPE":
+        """Construct from the flattened vocabulary (token i = tok_bytes[tok_off[i]:tok_off[i+1]], rank
+        tok_rank[i]) -- what `_b200pack.parse_tiktoken` produces from a `.tiktoken` file -- without a Python
+        dict of 100-200 k bytes objects ("next" row: vocabulary parsing, tiktoken/load.py:159-171).  The dict the
+        table-read methods need is built on first use."""
+        self = cls.__new__(cls)
+        blob = np.ascontiguousarray(tok_bytes, np.uint8)
+        off = np.ascontiguousarray(tok_off, np.uint64)
+        ranks = np.ascontiguousarray(tok_rank, np.uint32)
+        if len(off) != len(ranks) + 1 or (len(off) and int(off[-1]) > len(blob)):
+            raise ValueError("inconsistent flattened vocabulary")
+        self._create(blob if len(blob) else np.zeros(1, np.uint8), off, ranks, special_tokens, pat_str, device)
+        self._encoder_dict = None
+        self._flat = (blob, off, ranks)
+        return self
+
+    def _create(self, blob: np.ndarray, off: np.ndarray, ranks: np.ndarray, special_tokens: dict[str, int], pat_str: str,
+                device: int | None):
+        L = _lib.lib()
+        self._L = L
+        n_tok = len(ranks)
         self._special_names = list(special_tokens.keys())
         sblob, soff = _flatten_bytes([s.encode("utf-8") for s in self._special_names])
         sranks = np.asarray([special_tokens[s] for s in self._special_names], dtype=np.uint32)
@@ -83,16 +107,24 @@ class CoreBPE:
             import os
             device = int(os.environ.get("B200BPE_DEVICE", os.environ.get("LOCAL_RANK", "0")))
         h = C.c_void_p()
-        rc = L.b200bpe_create(_ptr(blob), _ptr(off), _ptr(ranks if len(ranks) else np.zeros(1, np.uint32)),
-                              len(toks), _ptr(sblob), _ptr(soff), _ptr(sranks), len(self._special_names),
+        rc = L.b200bpe_create(_ptr(blob), _ptr(off), _ptr(ranks if n_tok else np.zeros(1, np.uint32)),
+                              n_tok, _ptr(sblob), _ptr(soff), _ptr(sranks), len(self._special_names),
                               pat_str.encode("utf-8"), device, C.byref(h))
         _lib.check(rc)                      # ValueError for an unsupported pat_str / duplicate ranks
         self._h = h
         self.device = device
-        self._encoder = mergeable_ranks
         self._special = special_tokens
         self._decoder = None
+        self._flat = None
         self._lock = threading.Lock()
+
+    @property
+    def _encoder(self) -> dict[bytes, int]:
+        if self._encoder_dict is None:
+            blob, off, ranks = self._flat
+            raw, o = blob.tobytes(), off.tolist()
+            self._encoder_dict = {raw[o[i]:o[i + 1]]: r for i, r in enumerate(ranks.tolist())}
+        return self._encoder_dict
 
     def __del__(self):
         h = getattr(self, "_h", None)

@@ -60,6 +60,52 @@ class Encoding:
         self._special_token_values = set(special_tokens.values())
         self._core_bpe = _tiktoken.CoreBPE(mergeable_ranks, special_tokens, pat_str, device=device)
 
+    @classmethod
+    def from_tiktoken_file(cls, name: str, path_or_bytes, *, pat_str: str, special_tokens: dict[str, int],
+                           explicit_n_vocab: int | None = None, device: int | None = None) -> "Encoding":
+        """An Encoding straight from a `.tiktoken` vocabulary file (`base64(token) rank` per line, the format
+        `tiktoken/load.py:159-171` reads; `.gz` accepted), parsed in C into the flattened arrays the engine
+        takes -- the 100-200 k-entry Python dict is only built if something asks for it (pickling by value,
+        `encode_single_token`, `token_byte_values`)."""
+        from ._tiktoken import _b200pack
+        if isinstance(path_or_bytes, (bytes, bytearray, memoryview)):
+            data = bytes(path_or_bytes)
+        else:
+            with open(path_or_bytes, "rb") as f:
+                data = f.read()
+        if data[:2] == b"\x1f\x8b":
+            import gzip
+            data = gzip.decompress(data)
+        if _b200pack is None:                          # no C helper: the reference's own parse (load.py:159-171)
+            import base64
+            ranks = {base64.b64decode(tok): int(r) for tok, r in (ln.split() for ln in data.splitlines() if ln)}
+            return cls(name, pat_str=pat_str, mergeable_ranks=ranks, special_tokens=special_tokens,
+                       explicit_n_vocab=explicit_n_vocab, device=device)
+        blob, off, rk = _b200pack.parse_tiktoken(data)
+        blob, off, rk = np.frombuffer(blob, np.uint8), np.frombuffer(off, np.uint64), np.frombuffer(rk, np.uint32)
+        self = cls.__new__(cls)
+        self.name = name
+        self._pat_str = pat_str
+        self._ranks_dict = None
+        self._special_tokens = special_tokens
+        self.max_token_value = max(int(rk.max()) if len(rk) else 0, max(special_tokens.values(), default=0))
+        if explicit_n_vocab:
+            assert len(rk) + len(special_tokens) == explicit_n_vocab
+            assert self.max_token_value == explicit_n_vocab - 1
+        self._special_token_values = set(special_tokens.values())
+        self._core_bpe = _tiktoken.CoreBPE.from_flat(blob, off, rk, special_tokens, pat_str, device=device)
+        return self
+
+    @property
+    def _mergeable_ranks(self) -> dict[bytes, int]:
+        if self._ranks_dict is None:
+            self._ranks_dict = self._core_bpe._encoder
+        return self._ranks_dict
+
+    @_mergeable_ranks.setter
+    def _mergeable_ranks(self, value: dict[bytes, int]) -> None:
+        self._ranks_dict = value
+
     def __repr__(self) -> str:
         return f"<Encoding {self.name!r}>"
 

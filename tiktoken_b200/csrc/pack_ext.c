@@ -134,9 +134,72 @@ done:
     return ret;
 }
 
+
+/* parse_tiktoken(data: bytes) -> (blob: bytes, offsets: bytes uint64[n+1], ranks: bytes uint32[n])
+ * The `.tiktoken` vocabulary format of tiktoken/load.py:159-171 -- one "base64(token) rank" line per token --
+ * straight into the flattened arrays b200bpe_create takes, without a Python dict of 100-200 k bytes objects. */
+static PyObject *parse_tiktoken(PyObject *self, PyObject *arg) {
+    (void)self;
+    Py_buffer in;
+    if (PyObject_GetBuffer(arg, &in, PyBUF_SIMPLE) < 0) return NULL;
+    const unsigned char *p = (const unsigned char *)in.buf, *end = p + in.len;
+    signed char dec[256];
+    memset(dec, -1, sizeof dec);
+    for (int i = 0; i < 26; i++) { dec['A' + i] = (signed char)i; dec['a' + i] = (signed char)(26 + i); }
+    for (int i = 0; i < 10; i++) dec['0' + i] = (signed char)(52 + i);
+    dec['+'] = 62; dec['/'] = 63;
+    size_t n_lines = 0;
+    for (const unsigned char *q = p; q < end; q++) n_lines += (*q == '\n');
+    n_lines += 1;
+    unsigned char *blob = (unsigned char *)PyMem_Malloc((size_t)in.len + 4);       /* decoded bytes < input bytes */
+    uint64_t *off = (uint64_t *)PyMem_Malloc((n_lines + 1) * sizeof(uint64_t));
+    uint32_t *rank = (uint32_t *)PyMem_Malloc((n_lines + 1) * sizeof(uint32_t));
+    PyObject *ret = NULL;
+    if (!blob || !off || !rank) { PyErr_NoMemory(); goto done; }
+    {
+        size_t n = 0, nb = 0;
+        while (p < end) {
+            const unsigned char *eol = (const unsigned char *)memchr(p, '\n', (size_t)(end - p));
+            if (!eol) eol = end;
+            const unsigned char *le = eol;
+            if (le > p && le[-1] == '\r') le--;
+            if (le == p) { p = eol + 1; continue; }                                   /* empty line (load.py:165) */
+            const unsigned char *sp = (const unsigned char *)memchr(p, ' ', (size_t)(le - p));
+            if (!sp || sp == p || sp + 1 >= le) { PyErr_Format(PyExc_ValueError, "malformed line %zu", n + 1); goto done; }
+            off[n] = nb;
+            uint32_t acc = 0; int bits = 0;
+            const unsigned char *q = p;
+            for (; q < sp && *q != '='; q++) {
+                const int v = dec[*q];
+                if (v < 0) { PyErr_Format(PyExc_ValueError, "bad base64 on line %zu", n + 1); goto done; }
+                acc = (acc << 6) | (uint32_t)v; bits += 6;
+                if (bits >= 8) { bits -= 8; blob[nb++] = (unsigned char)(acc >> bits); acc &= (1u << bits) - 1u; }
+            }
+            for (; q < sp; q++) if (*q != '=') { PyErr_Format(PyExc_ValueError, "bad base64 padding on line %zu", n + 1); goto done; }
+            if (nb == off[n]) { PyErr_Format(PyExc_ValueError, "empty token on line %zu", n + 1); goto done; }
+            uint64_t r = 0;
+            for (q = sp + 1; q < le; q++) {
+                if (*q < '0' || *q > '9') { PyErr_Format(PyExc_ValueError, "bad rank on line %zu", n + 1); goto done; }
+                r = r * 10 + (uint64_t)(*q - '0');
+                if (r > 0xFFFFFFFFull) { PyErr_Format(PyExc_ValueError, "rank too large on line %zu", n + 1); goto done; }
+            }
+            rank[n++] = (uint32_t)r;
+            p = eol + 1;
+        }
+        off[n] = nb;
+        ret = Py_BuildValue("(y#y#y#)", (const char *)blob, (Py_ssize_t)nb, (const char *)off, (Py_ssize_t)((n + 1) * sizeof(uint64_t)),
+                            (const char *)rank, (Py_ssize_t)(n * sizeof(uint32_t)));
+    }
+done:
+    PyMem_Free(blob); PyMem_Free(off); PyMem_Free(rank);
+    PyBuffer_Release(&in);
+    return ret;
+}
+
 static PyMethodDef methods[] = {
     {"pack", pack, METH_O, "list[str] -> (utf8 blob bytes, uint64 offsets bytes)"},
     {"unpack", unpack, METH_VARARGS, "(tokens_addr, offsets_addr, n_docs) -> list[list[int]]"},
+    {"parse_tiktoken", parse_tiktoken, METH_O, "(.tiktoken file bytes) -> (blob, offsets uint64, ranks uint32)"},
     {"find_first", find_first, METH_VARARGS, "(blob, offsets, needles) -> None | (doc, needle_index, byte_pos)"},
     {NULL, NULL, 0, NULL}};
 static struct PyModuleDef mod = {PyModuleDef_HEAD_INIT, "_b200pack", "host marshalling helpers", -1, methods, NULL, NULL, NULL, NULL};
