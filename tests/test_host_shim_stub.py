@@ -223,3 +223,28 @@ def test_pickle_by_value_rebuilds_the_engine(enc):
     e, o, _, _ = enc
     e2 = pickle.loads(pickle.dumps(e))                           # tests/test_pickle.py
     assert e2.name == e.name and e2.encode_ordinary("hello world") == o.encode_ordinary("hello world")
+
+
+def test_registry_register_get_and_pickle_by_reference(enc, monkeypatch):
+    """tiktoken/registry.py behaviour: named constructors (here a locally registered one, as a tiktoken_ext plugin
+    would publish it), built once and cached; registered encodings pickle by name (tiktoken/core.py:409-417)."""
+    import tiktoken_b200
+    from tiktoken_b200 import registry
+    pat, ranks, special, _ = vu.load_encoding("r50k_base", allow_real=False)
+    calls = []
+
+    def ctor():
+        calls.append(1)
+        return {"name": "r50k_like_local", "pat_str": pat, "mergeable_ranks": ranks, "special_tokens": special}
+
+    monkeypatch.setattr(registry, "ENCODINGS", {})
+    registry.register_encoding("r50k_like_local", ctor)
+    assert "r50k_like_local" in tiktoken_b200.list_encoding_names()
+    e = tiktoken_b200.get_encoding("r50k_like_local")
+    assert tiktoken_b200.get_encoding("r50k_like_local") is e and len(calls) == 1
+    assert pickle.dumps(e) == pickle.dumps(e) and len(pickle.dumps(e)) < 400          # by reference, not 50 k tokens
+    assert pickle.loads(pickle.dumps(e)).encode_ordinary("hello") == e.encode_ordinary("hello")
+    with pytest.raises(ValueError, match="Unknown encoding"):
+        tiktoken_b200.get_encoding("no_such_encoding")
+    with pytest.raises(ValueError):
+        tiktoken_b200.get_encoding(5)
