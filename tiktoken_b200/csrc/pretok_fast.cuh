@@ -16,10 +16,13 @@ namespace b2bpe {
 
 struct SpanStats { unsigned long long positions, slow; };
 
-// Next-round rule, verified on the CPU (tests/test_pretok_rules.py builds the host check with it) but not yet
+// Next-round rules, verified on the CPU (tests/test_pretok_rules.py builds the host check with it) but not yet
 // measured / validated on the GPU: the shipped kernels are compiled with it OFF.
 #ifndef B2_O200K_FAST_PREFIX
 #define B2_O200K_FAST_PREFIX 0
+#endif
+#ifndef B2_CL100K_FAST_CONTRACTION
+#define B2_CL100K_FAST_CONTRACTION 0
 #endif
 
 #if defined(__CUDA_ARCH__)
@@ -164,7 +167,42 @@ B2_HD uint64_t span_fast(const TextAccess &t, int64_t w, uint64_t &slow_out, Spa
         // letters
         b |= L & (pN | pNL);
         b |= L & pX & ~pHi & ~(m.D << 1) & ((X | m.SP) << 2);
+#if B2_CL100K_FAST_CONTRACTION
+        // Letters next to an apostrophe a (the only undecided positions of English text).  The letter at a+1 needs
+        // nothing special: whether a starts `'s` or is the one-scalar prefix of a word, no piece starts at a+1
+        // when one starts at a, and the rule above covers an apostrophe inside a punctuation run.  The letters at
+        // a+2 / a+3 (behind letters) are where the first alternative `'(?i:[sdmt]|ll|ve|re)` may have ended:
+        //   boundary(a+2) = starts(a) & [sdmt](a+1);   boundary(a+3) = starts(a) & ![sdmt](a+1) & (ll|ve|re)(a+1,a+2)
+        // decided per apostrophe with two byte loads (apostrophes are sparse).  Non-ASCII letters in the suffix
+        // position (U+017F folds to s) stay with the general function.
+        slow |= L & (pX & pHi);
+        {
+            const uint64_t starts = m.APOS & (~(pX | pSP) | m.D);
+            const uint64_t cand = L & pL & aposNear & own;
+            uint64_t und = cand;
+            for (uint64_t aps = m.APOS & ((cand >> 2) | (cand >> 3)); aps;) {
+                const int j = B2_CTZLL(aps); aps &= aps - 1;
+                const uint64_t a1 = 1ull << (j + 1), a2 = a1 << 1, a3 = a2 << 1;
+                if (!(L & a1) || (m.hi & a1)) continue;                       // a+1 is not an ASCII letter
+                const bool st = (starts >> j) & 1ull;
+                const unsigned c1 = t.text[win0 + j + 1] | 0x20u;
+                const bool sdmt = c1 == 's' || c1 == 'd' || c1 == 'm' || c1 == 't';
+                if (cand & a2) {
+                    if (!(m.D & a1) && st && sdmt) b |= a2;
+                    und &= ~a2;
+                }
+                if ((cand & a3) && !(m.hi & a2)) {                              // a+2 is an ASCII letter (cand: letter before a+3)
+                    const unsigned c2 = t.text[win0 + j + 2] | 0x20u;
+                    const bool two = (c1 == 'l' && c2 == 'l') || (c1 == 'v' && c2 == 'e') || (c1 == 'r' && c2 == 'e');
+                    if (!(m.D & (a1 | a2)) && st && !sdmt && two) b |= a3;
+                    und &= ~a3;
+                }
+            }
+            slow |= und;
+        }
+#else
         slow |= L & ((pX & pHi) | pAPOS | (pL & aposNear));
+#endif
         // digits: groups of three from the run start
         b |= m.N & ~pN;
         {   // `\p{N}{1,3}`: a digit starts a piece iff the count of digits before it in its run is a
