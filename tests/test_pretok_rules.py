@@ -219,7 +219,7 @@ def _next_round_lib():
     csrc = os.path.join(ROOT, "tiktoken_b200", "csrc")
     so = os.path.join(csrc, "libb200bpe_hostcheck_next.so")
     subprocess.check_call(["g++", "-O2", "-fPIC", "-shared", "-std=c++17", "-DB2_O200K_FAST_PREFIX=1",
-                           "-DB2_CL100K_FAST_CONTRACTION=1", "-o", so, os.path.join(csrc, "hostcheck.cpp")])
+                           "-DB2_O200K_FAST_APOS=1", "-DB2_CL100K_FAST_CONTRACTION=1", "-o", so, os.path.join(csrc, "hostcheck.cpp")])
     H = C.CDLL(so)
     H.hc_piece_starts_fast.argtypes = [C.c_int, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
     return H, so
@@ -266,9 +266,10 @@ def test_next_round_cl100k_contraction_rule_is_exact():
 
 
 def test_next_round_o200k_prefix_rule_is_exact():
-    """pretok_fast.cuh carries one rule that is NOT in the shipped kernels yet (B2_O200K_FAST_PREFIX, off by
-    default until it has been measured and validated on the GPU): a letter after a punctuation scalar decided
-    bit-parallel as boundary(p) = !boundary(x).  Build the host check WITH it and hold it to the same standard
+    """pretok_fast.cuh carries rules that are NOT in the shipped kernels yet (B2_O200K_FAST_PREFIX,
+    B2_O200K_FAST_APOS; off by default until they have been measured and validated on the GPU): a letter after a
+    punctuation scalar decided bit-parallel as boundary(p) = !boundary(x), and apostrophes / contraction tails
+    decided per apostrophe.  Build the host check WITH it and hold it to the same standard
     as the shipped rules: exhaustive strings, the real engine's random Unicode splits, a mixed-script corpus,
     and a short fuzz run."""
     import subprocess
@@ -296,6 +297,24 @@ def test_next_round_o200k_prefix_rule_is_exact():
     got, off, _ = fast_starts(H, pid, docs)
     for i, d in enumerate(docs):
         assert np.array_equal(got[int(off[i]):int(off[i + 1])], expected_starts(o, d)), d
+    # apostrophes (B2_O200K_FAST_APOS): contraction tails of words, chains of them, apostrophes as prefixes / inside
+    # punctuation runs, every alignment
+    docs = []
+    for pad in range(0, 34):
+        for pre in ["x", "X", "1", " ", "!", "\n", "", "\u00e9", "\u4e2d", "\u0301", "/", "'", "a'", "a's", "a'll"]:
+            for suf in ["s", "S", "t", "d", "m", "ll", "lL", "ve", "re", "rE", "l", "v", "sx", "sX", "llx", "lx",
+                        "\u017f", "\u212a", "\u00e9", "1", " ", "!", ""]:
+                for post in ["", "a", " ", "'s", "B"]:
+                    docs.append(("z" * pad + pre + "'" + suf + post).encode())
+    got, off, _ = fast_starts(H, pid, docs)
+    for i, d in enumerate(docs):
+        assert np.array_equal(got[int(off[i]):int(off[i + 1])], expected_starts(o, d)), d
+    alphabet = ["a", "A", "s", "l", "e", "'", "!", " ", "\n", "1", "\u0301", "\u3042"]
+    for l in range(1, 5):
+        docs = ["".join(t).encode() for t in itertools.product(alphabet, repeat=l)]
+        got, off, _ = fast_starts(H, pid, docs)
+        for i, d in enumerate(docs):
+            assert np.array_equal(got[int(off[i]):int(off[i + 1])], expected_starts(o, d)), d
     cases = json.load(open(os.path.join(G, "splits_random.json")))["o200k"]
     docs = [bytes.fromhex(t) for t, _ in cases]
     got, off, _ = fast_starts(H, pid, docs)

@@ -21,6 +21,9 @@ struct SpanStats { unsigned long long positions, slow; };
 #ifndef B2_O200K_FAST_PREFIX
 #define B2_O200K_FAST_PREFIX 0
 #endif
+#ifndef B2_O200K_FAST_APOS
+#define B2_O200K_FAST_APOS 0
+#endif
 #ifndef B2_CL100K_FAST_CONTRACTION
 #define B2_CL100K_FAST_CONTRACTION 0
 #endif
@@ -250,9 +253,62 @@ B2_HD uint64_t span_fast(const TextAccess &t, int64_t w, uint64_t &slow_out, Spa
             const uint64_t letter_after_o = (low | m.LU) & pO;
             b |= letter_after_o & x0;
             slow |= letter_after_o & ~(x0 | x1);
+#if B2_O200K_FAST_APOS
+            // Apostrophes, and the letters up to three bytes behind one, decided per apostrophe (they are sparse):
+            //  * after a word character, `'s|'t|'re|'ve|'m|'ll|'d` (ASCII, any case) is the optional tail of that word's
+            //    piece: no piece starts at the apostrophe or inside the suffix, one starts right after it; anything else
+            //    makes the apostrophe an ordinary "other" scalar that starts a piece and prefixes the letters after it;
+            //  * after anything else it is an ordinary "other" scalar: boundary from the scalar before it, and the letter
+            //    after it gets the opposite (prefix rule above).
+            // Chains ('s'd: an apostrophe 2-3 bytes behind another), marks, slashes and non-ASCII suffix letters (U+017F)
+            // stay with the general function.
+            slow |= low & ((m.SLASH << 1) | pM);
+            slow |= m.LU & (pLB | pM | (m.SLASH << 1));
+            uint64_t und_after = (low | m.LU) & pAPOS & own;                                   // letter right after an apostrophe
+            uint64_t und_near = ((low & pL & aposNear) | (m.LU & (pLL | pLU) & aposNear)) & own;  // letter 2-3 bytes after, behind a letter
+            uint64_t und_apos = m.APOS & own;
+            for (uint64_t aps = m.APOS & (und_apos | (und_after >> 1) | (und_near >> 2) | (und_near >> 3)); aps;) {
+                const int j = B2_CTZLL(aps); aps &= aps - 1;
+                const uint64_t aj = 1ull << j, p1 = aj >> 1, a1 = aj << 1, a2 = aj << 2, a3 = aj << 3;
+                const bool at_d = (m.D & aj) != 0;
+                if (!at_d && ((m.M | unk0 | m.SLASH) & p1)) continue;
+                bool ba;                                   // does a piece start at the apostrophe
+                bool b1 = false, set1 = false, b2 = false, set2 = false, b3 = false, set3 = false;
+                if (!at_d && (L & p1)) {
+                    if (aposNear & aj) continue;                                                    // a chain
+                    if ((m.D & a1) || !(m.valid & a1)) ba = true;                                   // last scalar of its document
+                    else {
+                        if (m.hi & a1) continue;
+                        const bool l1 = (L & a1) != 0;
+                        const unsigned c1 = t.text[win0 + j + 1] | 0x20u;
+                        const bool sdmt = l1 && (c1 == 's' || c1 == 'd' || c1 == 'm' || c1 == 't');
+                        bool two = false;
+                        if (l1 && !sdmt && (L & a2) && !(m.hi & a2) && !(m.D & a2)) {
+                            const unsigned c2 = t.text[win0 + j + 2] | 0x20u;
+                            two = (c1 == 'l' && c2 == 'l') || (c1 == 'v' && c2 == 'e') || (c1 == 'r' && c2 == 'e');
+                        }
+                        if (sdmt) { ba = false; set1 = true; b1 = false; if ((L & a2) && !(m.D & a2)) { set2 = true; b2 = true; } }
+                        else if (two) { ba = false; set1 = true; b1 = false; set2 = true; b2 = false;
+                                        if ((L & a3) && !(m.D & a3)) { set3 = true; b3 = true; } }
+                        else { ba = true; if (l1) { set1 = true; b1 = false; } }
+                    }
+                } else {
+                    if (at_d || ((m.N | m.WS | m.NL) & p1)) ba = true;
+                    else if ((m.SP | m.O | m.APOS) & p1) ba = false;
+                    else continue;
+                    if ((L & a1) && !(m.D & a1)) { set1 = true; b1 = !ba; }
+                }
+                if (und_apos & aj) { b = ba ? (b | aj) : (b & ~aj); und_apos &= ~aj; }
+                if (und_after & a1) { if (set1) { b = b1 ? (b | a1) : (b & ~a1); und_after &= ~a1; } }
+                if (und_near & a2) { if (set2) b = b2 ? (b | a2) : (b & ~a2); und_near &= ~a2; }     // else: an ordinary letter
+                if (und_near & a3) { if (set3) b = b3 ? (b | a3) : (b & ~a3); und_near &= ~a3; }
+            }
+            slow |= und_apos | und_after | und_near;
+#else
             const uint64_t pXrest = (m.APOS | m.SLASH) << 1;
             slow |= low & (pXrest | pM | (pL & aposNear));
             slow |= m.LU & (pLB | pM | pXrest | ((pLL | pLU) & aposNear));
+#endif
         }
 #else
         b |= low & (pN | pNL);
@@ -260,7 +316,11 @@ B2_HD uint64_t span_fast(const TextAccess &t, int64_t w, uint64_t &slow_out, Spa
         b |= m.LU & (pLL | pN | pNL);
         slow |= m.LU & (pLB | pM | pXo | ((pLL | pLU) & aposNear));
 #endif
+#if B2_O200K_FAST_PREFIX && B2_O200K_FAST_APOS
+        slow |= m.M | m.SLASH;
+#else
         slow |= m.M | m.APOS | m.SLASH;
+#endif
         b |= m.O & (pL | pN | ((m.WS | m.NL) << 1));
         slow |= m.O & (pM | (m.SLASH << 1));
         b |= m.N & ~pN;
