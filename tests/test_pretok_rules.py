@@ -219,7 +219,7 @@ def _next_round_lib():
     csrc = os.path.join(ROOT, "tiktoken_b200", "csrc")
     so = os.path.join(csrc, "libb200bpe_hostcheck_next.so")
     subprocess.check_call(["g++", "-O2", "-fPIC", "-shared", "-std=c++17", "-DB2_O200K_FAST_PREFIX=1",
-                           "-DB2_O200K_FAST_APOS=1", "-DB2_CL100K_FAST_CONTRACTION=1", "-o", so, os.path.join(csrc, "hostcheck.cpp")])
+                           "-DB2_O200K_FAST_APOS=1", "-DB2_CL100K_FAST_CONTRACTION=1", "-DB2_R50K_FAST_CONTRACTION=1", "-o", so, os.path.join(csrc, "hostcheck.cpp")])
     H = C.CDLL(so)
     H.hc_piece_starts_fast.argtypes = [C.c_int, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
     return H, so
@@ -263,6 +263,37 @@ def test_next_round_cl100k_contraction_rule_is_exact():
     for i, d in enumerate(cdocs):
         assert np.array_equal(got[int(off[i]):int(off[i + 1])], expected_starts(o, d))
     assert st[1] * 1000 < st[0]                 # < 0.1 % undecided (0.42 % without the rule)
+
+
+def test_next_round_r50k_contraction_rule_is_exact():
+    """B2_R50K_FAST_CONTRACTION (off in the shipped kernels): the case-sensitive `'(?:[sdmt]|ll|ve|re)` of the
+    r50k / p50k pattern decided per apostrophe.  Documents are packed back to back, so apostrophes also meet
+    across document boundaries (the case that needed care)."""
+    H, _ = _next_round_lib()
+    pid, pat = PATS["r50k"]
+    o = Oracle(BYTES, {}, pat)
+    spec = json.load(open(os.path.join(G, "splits_exhaustive.json")))["r50k"]
+    alphabet = spec["alphabet"] + ["v", "e", "r", "S", "\u00e9"]
+    for l in range(1, 5):
+        docs = ["".join(t).encode() for t in itertools.product(alphabet, repeat=l)]
+        got, off, _ = fast_starts(H, pid, docs)
+        for i, d in enumerate(docs):
+            assert np.array_equal(got[int(off[i]):int(off[i + 1])], expected_starts(o, d)), d
+    docs = []
+    for pad in range(40):
+        for pre in ["x", "1", " ", "!", "\n", "", "\u00e9", "'"]:
+            for suf in ["s", "S", "t", "d", "m", "ll", "LL", "lL", "ve", "re", "rE", "l", "v", "sx", "llx", "lx", "\u017f",
+                        "\u00e9a", "\u4e2da", "1", ""]:
+                for post in ["", "a", " ", "'s", "1"]:
+                    docs.append(("z" * pad + pre + "'" + suf + post).encode())
+    got, off, _ = fast_starts(H, pid, docs)
+    for i, d in enumerate(docs):
+        assert np.array_equal(got[int(off[i]):int(off[i + 1])], expected_starts(o, d)), d
+    cases = json.load(open(os.path.join(G, "splits_random.json")))["r50k"]
+    docs = [bytes.fromhex(t) for t, _ in cases]
+    got, off, _ = fast_starts(H, pid, docs)
+    for i, d in enumerate(docs):
+        assert np.array_equal(got[int(off[i]):int(off[i + 1])], expected_starts(o, d)), d
 
 
 def test_next_round_o200k_prefix_rule_is_exact():

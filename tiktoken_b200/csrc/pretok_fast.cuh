@@ -24,6 +24,9 @@ struct SpanStats { unsigned long long positions, slow; };
 #ifndef B2_O200K_FAST_APOS
 #define B2_O200K_FAST_APOS 0
 #endif
+#ifndef B2_R50K_FAST_CONTRACTION
+#define B2_R50K_FAST_CONTRACTION 0
+#endif
 #ifndef B2_CL100K_FAST_CONTRACTION
 #define B2_CL100K_FAST_CONTRACTION 0
 #endif
@@ -161,7 +164,37 @@ B2_HD uint64_t span_fast(const TextAccess &t, int64_t w, uint64_t &slow_out, Spa
         b |= WSany & (~pWSany | nextNonWs);
         slow |= WSany & m.hi & pWSany;
         b |= L & ~(pL | pSP);
+#if B2_R50K_FAST_CONTRACTION
+        // Letters up to three bytes behind an apostrophe a, decided per apostrophe.  `'(?:[sdmt]|ll|ve|re)` is the first
+        // alternative and case-sensitive ASCII: when a piece starts at a and the suffix matches, the suffix letters
+        // continue that piece and the next letter starts one; otherwise the apostrophe is punctuation and the letter
+        // after it starts a word (the default of the rule above).
+        {
+            const uint64_t starts = m.APOS & (~(pX | pSP) | m.D);
+            uint64_t und_after = L & pAPOS & own, und_near = L & pL & aposNear & own;
+            for (uint64_t aps = m.APOS & ((und_after >> 1) | (und_near >> 2) | (und_near >> 3)); aps;) {
+                const int j = B2_CTZLL(aps); aps &= aps - 1;
+                const uint64_t a1 = 1ull << (j + 1), a2 = a1 << 1, a3 = a2 << 1;
+                bool c1ok = false, c2ok = false;                       // 1-letter / 2-letter contraction at this apostrophe
+                if ((L & a1) && !(m.hi & a1) && !(m.D & a1) && ((starts >> j) & 1ull)) {
+                    const unsigned c1 = t.text[win0 + j + 1];
+                    c1ok = c1 == 's' || c1 == 'd' || c1 == 'm' || c1 == 't';
+                    if (!c1ok && (L & a2) && !(m.hi & a2) && !(m.D & a2)) {
+                        const unsigned c2 = t.text[win0 + j + 2];
+                        c2ok = (c1 == 'l' && c2 == 'l') || (c1 == 'v' && c2 == 'e') || (c1 == 'r' && c2 == 'e');
+                    }
+                }
+                if (und_after & a1) { if (c1ok || c2ok) b &= ~a1; und_after &= ~a1; }
+                if (und_near & a2) { if (c1ok) b |= a2; und_near &= ~a2; }
+                // a+3 is this apostrophe's business only behind two letters; behind another apostrophe at a+1 (it may start
+                // a document) it is that one's
+                if ((und_near & a3) && !(m.APOS & a1)) { if (c2ok) b |= a3; und_near &= ~a3; }
+            }
+            slow |= und_after | und_near;
+        }
+#else
         slow |= L & (pAPOS | (pL & aposNear));
+#endif
         b |= m.N & ~(pN | pSP);
         b |= X & ~(pX | pSP);
     } else if (PAT == PAT_CL100K) {
