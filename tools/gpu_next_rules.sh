@@ -17,7 +17,7 @@ for v in a b; do
   timeout 400 python tools/gpu_check.py > gpurun_out/check_$v.log 2>&1; echo "gpu_check rc=$?"; tail -1 gpurun_out/check_$v.log
   timeout 600 python -m pytest tests -x -q -m gpu > gpurun_out/pytest_$v.log 2>&1; echo "pytest rc=$?"; tail -1 gpurun_out/pytest_$v.log
   echo config2; run
-  echo "config2 text, o200k"; run --workload config3 --bytes 268435456
+  echo config3; run --workload config3 --bytes 268435456
   echo config5; run --workload config5 --bytes 268435456
 done
 cp /tmp/a.so tiktoken_b200/csrc/libb200bpe.so
