@@ -219,14 +219,15 @@ def _next_round_lib():
     csrc = os.path.join(ROOT, "tiktoken_b200", "csrc")
     so = os.path.join(csrc, "libb200bpe_hostcheck_next.so")
     subprocess.check_call(["g++", "-O2", "-fPIC", "-shared", "-std=c++17", "-DB2_O200K_FAST_PREFIX=1",
-                           "-DB2_O200K_FAST_APOS=1", "-DB2_CL100K_FAST_CONTRACTION=1", "-DB2_R50K_FAST_CONTRACTION=1", "-o", so, os.path.join(csrc, "hostcheck.cpp")])
+                           "-DB2_O200K_FAST_APOS=1", "-DB2_CL100K_FAST_CONTRACTION=1", "-DB2_R50K_FAST_CONTRACTION=1",
+                           "-DB2_CL100K_FAST_WSNL=1", "-o", so, os.path.join(csrc, "hostcheck.cpp")])
     H = C.CDLL(so)
     H.hc_piece_starts_fast.argtypes = [C.c_int, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
     return H, so
 
 
 def test_next_round_cl100k_contraction_rule_is_exact():
-    """The second rule that is NOT in the shipped kernels yet (B2_CL100K_FAST_CONTRACTION, off by default):
+    """Rules that are NOT in the shipped kernels yet (B2_CL100K_FAST_CONTRACTION, B2_CL100K_FAST_WSNL; off by default):
     letters 2..3 bytes after an apostrophe decided per apostrophe (is it 's|'t|'re|'ve|'m|'ll|'d, where does it
     end) instead of by the general function.  Same standard as the shipped rules; with it English text has no
     undecided position left."""
@@ -250,6 +251,23 @@ def test_next_round_cl100k_contraction_rule_is_exact():
     got, off, _ = fast_starts(H, pid, docs)
     for i, d in enumerate(docs):
         assert np.array_equal(got[int(off[i]):int(off[i + 1])], expected_starts(o, d)), d
+    # B2_CL100K_FAST_WSNL: whitespace right after CR/LF (indentation), runs shorter and longer than the window,
+    # CR/LF runs behind punctuation, document ends
+    docs = []
+    for pad in range(0, 40, 3):
+        for pre in ["x", "!", "!\n", "x\n\n", "!\r\n\n", "", "/\n"]:
+            for nl in ["\n", "\r\n", "\n" * 10]:
+                for ws in [" ", "    ", "\t", " " * 9, " " * 20, " " * 45, "\u3000", " \u3000"]:
+                    for post in ["x", "\n", "\nx", "", "!", "\n\n  y"]:
+                        docs.append(("z" * pad + pre + nl + ws + post).encode())
+    got, off, _ = fast_starts(H, pid, docs)
+    for i, d in enumerate(docs):
+        assert np.array_equal(got[int(off[i]):int(off[i + 1])], expected_starts(o, d)), d
+    for l in range(1, 6):
+        docs = ["".join(t).encode() for t in itertools.product(["a", " ", "\t", "\n", "\r", "!", "/"], repeat=l)]
+        got, off, _ = fast_starts(H, pid, docs)
+        for i, d in enumerate(docs):
+            assert np.array_equal(got[int(off[i]):int(off[i + 1])], expected_starts(o, d)), d
     cases = json.load(open(os.path.join(G, "splits_random.json")))["cl100k"]
     docs = [bytes.fromhex(t) for t, _ in cases]
     got, off, _ = fast_starts(H, pid, docs)

@@ -27,6 +27,9 @@ struct SpanStats { unsigned long long positions, slow; };
 #ifndef B2_R50K_FAST_CONTRACTION
 #define B2_R50K_FAST_CONTRACTION 0
 #endif
+#ifndef B2_CL100K_FAST_WSNL
+#define B2_CL100K_FAST_WSNL 0
+#endif
 #ifndef B2_CL100K_FAST_CONTRACTION
 #define B2_CL100K_FAST_CONTRACTION 0
 #endif
@@ -262,7 +265,59 @@ B2_HD uint64_t span_fast(const TextAccess &t, int64_t w, uint64_t &slow_out, Spa
         b |= m.NL & (pL | pN);
         b |= WSnn & ~pWSany;
         b |= WSnn & pWSnn & nextNonWs;
+#if B2_CL100K_FAST_WSNL
+        // Whitespace right after CR/LF (the first indentation character of every line of code).  `\s++$` / `\s*[\r\n]`
+        // swallow it iff its whitespace run reaches the document end or another CR/LF; then it still starts a piece
+        // when the CR/LFs before it were the `[\r\n]*+` tail of a punctuation piece.  Both are reachability questions
+        // along runs: solved for all positions at once by propagating seeds through run links with doubling shifts;
+        // runs that leave the window stay with the general function.
+        slow |= WSnn & m.hi & pWSany;
+        {
+            const uint64_t cand = WSnn & pNL & own;
+            if (cand) {
+                const uint64_t nd1 = ~(m.D >> 1);                                   // no document starts at i+1
+                const int64_t last = t.n - 1 - win0;                                // the window's last byte is NOT an end
+                const uint64_t text_end = (last >= 0 && last < 48) ? (1ull << last) : 0ull;
+                const uint64_t end_after = m.valid & ((m.D >> 1) | text_end);       // i is the last byte of its document
+                const uint64_t known_cls = m.valid & ~unk0;
+                // forward: SW = whitespace from which only whitespace leads to a CR/LF or to the document end;
+                //          KN = whitespace whose run ends (in anything known) inside the window
+                uint64_t sw = WSnn & (((m.NL >> 1) & nd1) | end_after);
+                uint64_t kn = WSnn & ((((known_cls & ~WSnn) >> 1) & nd1) | end_after);
+                uint64_t link = WSnn & (WSnn >> 1) & nd1;                           // i and i+1: whitespace of one document
+                sw |= link & (sw >> 1); kn |= link & (kn >> 1);
+                uint64_t l2 = link & (link >> 1);
+                sw |= l2 & (sw >> 2); kn |= l2 & (kn >> 2);
+                uint64_t l4 = l2 & (l2 >> 2);
+                sw |= l4 & (sw >> 4); kn |= l4 & (kn >> 4);
+                uint64_t l8 = l4 & (l4 >> 4);
+                sw |= l8 & (sw >> 8); kn |= l8 & (kn >> 8);
+                uint64_t l16 = l8 & (l8 >> 8);
+                sw |= l16 & (sw >> 16); kn |= l16 & (kn >> 16);
+                uint64_t l32 = l16 & (l16 >> 16);
+                sw |= l32 & (sw >> 32); kn |= l32 & (kn >> 32);
+                // backward: TL = CR/LF reached from a punctuation scalar through CR/LFs only;  KB = CR/LF whose run
+                //           starts (after anything known, or at a document start) inside the window
+                const uint64_t oth = m.O | m.M | m.APOS | m.SLASH;
+                const uint64_t nd0 = ~m.D;                                         // i does not start a document
+                uint64_t tl = m.NL & (oth << 1) & nd0;
+                uint64_t kb = m.NL & ((((known_cls & ~m.NL) << 1)) | m.D);
+                uint64_t bl = m.NL & (m.NL << 1) & nd0;                            // i-1 and i: CR/LF of one document
+                tl |= bl & (tl << 1); kb |= bl & (kb << 1);
+                uint64_t b2 = bl & (bl << 1);
+                tl |= b2 & (tl << 2); kb |= b2 & (kb << 2);
+                uint64_t b4 = b2 & (b2 << 2);
+                tl |= b4 & (tl << 4); kb |= b4 & (kb << 4);
+                const uint64_t fwd_known = kn, swl = sw;
+                // decided: run end known, and either not swallowed or the CR/LF run before it is known too
+                const uint64_t dec = cand & fwd_known & (~swl | (kb << 1));
+                b |= dec & (~swl | (tl << 1));
+                slow |= cand & ~dec;
+            }
+        }
+#else
         slow |= WSnn & (pNL | (m.hi & pWSany));
+#endif
     } else {
         const uint64_t Xo = m.O | m.APOS | m.SLASH;
         const uint64_t pXo = Xo << 1, pM = m.M << 1, pLB = m.LB << 1, pLL = m.LL << 1, pLU = m.LU << 1;
