@@ -220,7 +220,7 @@ def _next_round_lib():
     so = os.path.join(csrc, "libb200bpe_hostcheck_next.so")
     subprocess.check_call(["g++", "-O2", "-fPIC", "-shared", "-std=c++17", "-DB2_O200K_FAST_PREFIX=1",
                            "-DB2_O200K_FAST_APOS=1", "-DB2_CL100K_FAST_CONTRACTION=1", "-DB2_R50K_FAST_CONTRACTION=1",
-                           "-DB2_CL100K_FAST_WSNL=1", "-o", so, os.path.join(csrc, "hostcheck.cpp")])
+                           "-DB2_CL100K_FAST_WSNL=1", "-DB2_O200K_FAST_WSNL=1", "-o", so, os.path.join(csrc, "hostcheck.cpp")])
     H = C.CDLL(so)
     H.hc_piece_starts_fast.argtypes = [C.c_int, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
     return H, so
@@ -355,6 +355,17 @@ def test_next_round_o200k_prefix_rule_is_exact():
                         "\u017f", "\u212a", "\u00e9", "1", " ", "!", ""]:
                 for post in ["", "a", " ", "'s", "B"]:
                     docs.append(("z" * pad + pre + "'" + suf + post).encode())
+    got, off, _ = fast_starts(H, pid, docs)
+    for i, d in enumerate(docs):
+        assert np.array_equal(got[int(off[i]):int(off[i + 1])], expected_starts(o, d)), d
+    # B2_O200K_FAST_WSNL: whitespace right after CR/LF; CR/LF runs behind punctuation / slashes / marks
+    docs = []
+    for pad in range(0, 40, 4):
+        for pre in ["x", "!", "!\n", "x\n\n", "", "/\n", "!\n/", "a/", "x\u0301", "!\u0301"]:
+            for nl in ["\n", "\r\n", "\n" * 10, "\n/\n"]:
+                for ws in [" ", "    ", "\t", " " * 9, " " * 20, " " * 45, "\u3000"]:
+                    for post in ["x", "\n", "\nx", "", "!", "\n\n  y"]:
+                        docs.append(("z" * pad + pre + nl + ws + post).encode())
     got, off, _ = fast_starts(H, pid, docs)
     for i, d in enumerate(docs):
         assert np.array_equal(got[int(off[i]):int(off[i + 1])], expected_starts(o, d)), d

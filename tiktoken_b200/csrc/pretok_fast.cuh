@@ -27,6 +27,9 @@ struct SpanStats { unsigned long long positions, slow; };
 #ifndef B2_R50K_FAST_CONTRACTION
 #define B2_R50K_FAST_CONTRACTION 0
 #endif
+#ifndef B2_O200K_FAST_WSNL
+#define B2_O200K_FAST_WSNL 0
+#endif
 #ifndef B2_CL100K_FAST_WSNL
 #define B2_CL100K_FAST_WSNL 0
 #endif
@@ -433,7 +436,51 @@ B2_HD uint64_t span_fast(const TextAccess &t, int64_t w, uint64_t &slow_out, Spa
         slow |= m.NL & pM;
         b |= WSnn & ~pWSany;
         b |= WSnn & pWSnn & nextNonWs;
+#if B2_O200K_FAST_WSNL
+        // Whitespace right after CR/LF, as in the cl100k rule above, with o200k's alternatives: `\s*[\r\n]+` swallows
+        // it iff another CR/LF follows in its whitespace run (the document end does not); it still starts a piece when
+        // the CR/LFs before it are the `[\r\n/]*` tail of a punctuation piece, i.e. directly follow an "other" scalar,
+        // apostrophe or slash.  A mark before the CR/LFs may belong to a word: left to the general function.
+        slow |= WSnn & m.hi & pWSany;
+        {
+            const uint64_t cand = WSnn & pNL & own;
+            if (cand) {
+                const uint64_t nd1 = ~(m.D >> 1);
+                const int64_t last = t.n - 1 - win0;
+                const uint64_t text_end = (last >= 0 && last < 48) ? (1ull << last) : 0ull;
+                const uint64_t end_after = m.valid & ((m.D >> 1) | text_end);
+                const uint64_t known_cls = m.valid & ~unk0;
+                uint64_t sw = WSnn & (m.NL >> 1) & nd1;
+                uint64_t kn = WSnn & ((((known_cls & ~WSnn) >> 1) & nd1) | end_after);
+                uint64_t link = WSnn & (WSnn >> 1) & nd1;
+                sw |= link & (sw >> 1); kn |= link & (kn >> 1);
+                uint64_t l2 = link & (link >> 1);
+                sw |= l2 & (sw >> 2); kn |= l2 & (kn >> 2);
+                uint64_t l4 = l2 & (l2 >> 2);
+                sw |= l4 & (sw >> 4); kn |= l4 & (kn >> 4);
+                uint64_t l8 = l4 & (l4 >> 4);
+                sw |= l8 & (sw >> 8); kn |= l8 & (kn >> 8);
+                uint64_t l16 = l8 & (l8 >> 8);
+                sw |= l16 & (sw >> 16); kn |= l16 & (kn >> 16);
+                uint64_t l32 = l16 & (l16 >> 16);
+                sw |= l32 & (sw >> 32); kn |= l32 & (kn >> 32);
+                const uint64_t nd0 = ~m.D;
+                uint64_t tl = m.NL & (Xo << 1) & nd0;
+                uint64_t kb = m.NL & (((known_cls & ~m.NL & ~m.M) << 1) | m.D);
+                uint64_t bl = m.NL & (m.NL << 1) & nd0;
+                tl |= bl & (tl << 1); kb |= bl & (kb << 1);
+                uint64_t b2 = bl & (bl << 1);
+                tl |= b2 & (tl << 2); kb |= b2 & (kb << 2);
+                uint64_t b4 = b2 & (b2 << 2);
+                tl |= b4 & (tl << 4); kb |= b4 & (kb << 4);
+                const uint64_t dec = cand & kn & (~sw | (kb << 1));
+                b |= dec & (~sw | (tl << 1));
+                slow |= cand & ~dec;
+            }
+        }
+#else
         slow |= WSnn & (pNL | (m.hi & pWSany));
+#endif
     }
     // anything that touches an undecoded (truncated / unknown) non-ASCII byte goes the slow way
     const uint64_t unk = unk0;

@@ -1,9 +1,9 @@
 #!/bin/bash
 # Round-2 starter (run under gpurun): A/B of the shipped library against one built with the next-round pre-tokeniser
-# rules (B2_O200K_FAST_PREFIX, B2_O200K_FAST_APOS, B2_CL100K_FAST_CONTRACTION, B2_R50K_FAST_CONTRACTION, B2_CL100K_FAST_WSNL -- CPU-verified,
+# rules (B2_O200K_FAST_PREFIX, B2_O200K_FAST_APOS, B2_CL100K_FAST_CONTRACTION, B2_R50K_FAST_CONTRACTION, B2_CL100K_FAST_WSNL, B2_O200K_FAST_WSNL -- CPU-verified,
 # see tests/test_pretok_rules.py).  Build the variant HERE first (nvcc cross-compiles without a GPU):
 #   cd tiktoken_b200/csrc && nvcc -DB2_O200K_FAST_PREFIX=1 -DB2_O200K_FAST_APOS=1 -DB2_CL100K_FAST_CONTRACTION=1 \
-#      -DB2_R50K_FAST_CONTRACTION=1 -DB2_CL100K_FAST_WSNL=1 -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -shared \
+#      -DB2_R50K_FAST_CONTRACTION=1 -DB2_CL100K_FAST_WSNL=1 -DB2_O200K_FAST_WSNL=1 -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -shared \
 #      -Xcompiler -fPIC -o libvariant_b.so b200bpe.cu
 # then: gpurun --timeout 1500 -- 'bash tools/gpu_next_rules.sh'.  Parity first (gpu_check + pytest -m gpu on the variant),
 # then the four workloads for both builds.  Adopt the flags in tiktoken_b200/_lib.py:NVCC_FLAGS only if parity is green.
