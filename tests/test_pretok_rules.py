@@ -212,10 +212,15 @@ def test_malformed_utf8_terminates(hostcheck):
             assert len(got) == n
 
 
+_NEXT_LIB = []
+
+
 def _next_round_lib():
     import ctypes as C
     import subprocess
     from conftest import ROOT
+    if _NEXT_LIB:
+        return _NEXT_LIB[0]
     csrc = os.path.join(ROOT, "tiktoken_b200", "csrc")
     so = os.path.join(csrc, "libb200bpe_hostcheck_next.so")
     subprocess.check_call(["g++", "-O2", "-fPIC", "-shared", "-std=c++17", "-DB2_O200K_FAST_PREFIX=1",
@@ -223,6 +228,7 @@ def _next_round_lib():
                            "-DB2_CL100K_FAST_WSNL=1", "-DB2_O200K_FAST_WSNL=1", "-o", so, os.path.join(csrc, "hostcheck.cpp")])
     H = C.CDLL(so)
     H.hc_piece_starts_fast.argtypes = [C.c_int, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
+    _NEXT_LIB.append((H, so))
     return H, so
 
 
