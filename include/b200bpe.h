@@ -105,6 +105,10 @@ int b200bpe_last_timings(b200bpe_t *h, float *ms9, uint32_t *n_launches);
  * [2] long-token table + blob, [3] Unicode class tables. */
 int b200bpe_table_bytes(b200bpe_t *h, uint64_t *bytes4);
 
+/* Number of CUDA devices the library can see (0 when there is none: every constructor then fails with
+ * B200BPE_ECUDA -- there is no CPU fallback). */
+int b200bpe_device_count(void);
+
 const char *b200bpe_last_error(void);
 const char *b200bpe_version(void);
 

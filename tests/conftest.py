@@ -46,9 +46,28 @@ def hostcheck():
     return H
 
 
+_HAVE_GPU = None
+
+
 def have_gpu() -> bool:
-    try:
-        import torch
-        return torch.cuda.is_available()
-    except Exception:
-        return False
+    """CUDA device present?  Asked of the engine's own library (cudaGetDeviceCount), not of torch: the
+    engine does not need torch."""
+    global _HAVE_GPU
+    if _HAVE_GPU is None:
+        try:
+            from tiktoken_b200 import _lib
+            _lib.build()
+            _HAVE_GPU = int(_lib.lib().b200bpe_device_count()) > 0
+        except Exception:
+            _HAVE_GPU = False
+    return _HAVE_GPU
+
+
+def pytest_collection_modifyitems(config, items):
+    """`-m gpu` tests are skipped (not failed) on a machine without a CUDA device."""
+    if have_gpu():
+        return
+    skip = pytest.mark.skip(reason="needs a CUDA device (the engine has no CPU fallback)")
+    for item in items:
+        if "gpu" in item.keywords:
+            item.add_marker(skip)

@@ -23,7 +23,6 @@ def get(enc):
     if enc not in _cache:
         import tiktoken_b200
         from oracle import Oracle
-        assert have_gpu(), "GPU tests need a CUDA device"
         pat, ranks, special, src = vu.load_encoding(enc, allow_real=False)
         e = tiktoken_b200.Encoding(enc + "_syn", pat_str=pat, mergeable_ranks=ranks, special_tokens=special)
         _cache[enc] = (e, Oracle(ranks, special, pat), special)

@@ -1,0 +1,226 @@
+"""Parity of the paths the plain parity suite does not reach ("parity holes"):
+  * the chunked host pipeline (3-slot H2D / kernels / D2H) with chunk seams, forced by B200BPE_CHUNK_MB=1
+    and, at the default chunk size, by an input of > 200 MiB -- every token compared with the oracle;
+  * one device-resident call of > 256 MiB (the large-batch workspace path) compared in full;
+  * pieces of 4 097 ... 100 000 bytes on adversarial tiny-alphabet vocabularies (rank ties, cascades,
+    non-monotone ranks) through the block / cluster round-synchronous merge (ref src/lib.rs:47-138);
+  * result lifetime (TokenBuffer / arrays outliving the Encoding);
+  * the reference's OWN host class (`tiktoken.core.Encoding`, unmodified, from the installed wheel) running on
+    top of `tiktoken_b200._tiktoken` -- the true drop-in.
+All through the C ABI, bit-exact."""
+import gc
+import os
+import pickle
+import random
+
+import numpy as np
+import pytest
+
+import vocab_util as vu
+from tools import corpus
+
+pytestmark = pytest.mark.gpu
+CORES = os.cpu_count() or 1
+
+
+def _oracle(ranks, special, pat):
+    from oracle import Oracle
+    return Oracle(ranks, special, pat)
+
+
+def _chunked_encoding(enc_name, chunk_mb):
+    """An Encoding whose host pipeline cuts batches into chunk_mb-MiB chunks (read at construction)."""
+    import tiktoken_b200
+    pat, ranks, special, _ = vu.load_encoding(enc_name, allow_real=False)
+    old = os.environ.get("B200BPE_CHUNK_MB")
+    os.environ["B200BPE_CHUNK_MB"] = str(chunk_mb)
+    try:
+        e = tiktoken_b200.Encoding(enc_name + "_chunk", pat_str=pat, mergeable_ranks=ranks, special_tokens=special)
+    finally:
+        if old is None:
+            os.environ.pop("B200BPE_CHUNK_MB", None)
+        else:
+            os.environ["B200BPE_CHUNK_MB"] = old
+    return e, _oracle(ranks, special, pat), special
+
+
+def _same(buf, exp_t, exp_o):
+    ok = np.array_equal(buf.tokens(), exp_t) and np.array_equal(buf.offsets(), exp_o)
+    buf.close()
+    return ok
+
+
+@pytest.mark.parametrize("enc,kind", [("cl100k_base", corpus.ENGLISH), ("o200k_base", corpus.MIXED),
+                                      ("p50k_base", corpus.CODE), ("r50k_base", corpus.ENGLISH)])
+def test_chunk_seams_1mib_chunks(enc, kind):
+    e, o, special = _chunked_encoding(enc, 1)
+    text = corpus.generate(kind, 99, 7 << 20)
+    layouts = [corpus.docs_fixed(text, 65536, at_space=False)[1],                       # ~16 docs per chunk
+               corpus.docs_fixed(text, 300_000, at_space=False)[1],                     # docs that do not divide a chunk
+               np.asarray([0, 10, 10, 3 << 20, (3 << 20) + 5, len(text)], np.uint64)]   # docs larger than a chunk, empty doc
+    lens = np.clip(np.rint(np.random.default_rng(3).lognormal(np.log(90), 0.5, size=200_000)), 0, 2000).astype(np.int64)
+    layouts.append(corpus.docs_from_lengths(text, lens[:int(np.searchsorted(np.cumsum(lens), len(text)))], False)[1])
+    for off in layouts:
+        off = np.ascontiguousarray(off, np.uint64)
+        # cut points must not split a UTF-8 scalar: move them back onto lead bytes
+        for i in range(1, len(off) - 1):
+            while 0 < off[i] < len(text) and (text[int(off[i])] & 0xC0) == 0x80:
+                off[i] -= 1
+        off = np.maximum.accumulate(off)
+        exp_t, exp_o = o.encode_ordinary_batch_np(text, off, CORES)
+        assert _same(e.encode_ordinary_packed(text, off), exp_t, exp_o)
+    # allowed specials across chunk seams (CoreBPE::encode, lib.rs:375-442)
+    names = sorted(special)
+    rnd = random.Random(5)
+    docs = []
+    for d in range(40):
+        s = text[d * 150_000:(d + 1) * 150_000].tobytes().decode("utf-8", "ignore")
+        cut = sorted(rnd.sample(range(len(s)), 20))
+        parts, prev = [], 0
+        for c in cut:
+            parts += [s[prev:c], rnd.choice(names)]
+            prev = c
+        docs.append("".join(parts) + s[prev:])
+    got = e.encode_batch(docs, allowed_special="all")
+    assert got == [o.encode(d, set(special)) for d in docs]
+
+
+def test_default_chunks_over_200mib_full_compare():
+    import tiktoken_b200
+    pat, ranks, special, _ = vu.load_encoding("cl100k_base", allow_real=False)
+    e = tiktoken_b200.Encoding("big_host", pat_str=pat, mergeable_ranks=ranks, special_tokens=special)
+    o = _oracle(ranks, special, pat)
+    text, off = corpus.config2(nbytes=208 << 20, seed=4321)
+    exp_t, exp_o = o.encode_ordinary_batch_np(text, off, CORES)
+    assert _same(e.encode_ordinary_packed(text, off), exp_t, exp_o)
+    # the same bytes as ONE document (chunking cannot cut it, one pipeline pass takes it whole): checked through
+    # the round trip decode(encode(x)) == x on the device decoder (the oracle is single-threaded on one document)
+    one = np.asarray([0, len(text)], np.uint64)
+    buf = e.encode_ordinary_packed(text, one)
+    toks, toff = np.array(buf.tokens()), np.array(buf.offsets())
+    buf.close()
+    assert int(toff[-1]) == len(toks) and len(toff) == 2
+    data, boff = e.decode_packed(toks, toff)
+    assert np.array_equal(data, text) and np.array_equal(boff, one)
+
+
+def test_device_resident_call_over_256mib_full_compare():
+    import torch
+    import tiktoken_b200
+    pat, ranks, special, _ = vu.load_encoding("o200k_base", allow_real=False)
+    e = tiktoken_b200.Encoding("big_dev", pat_str=pat, mergeable_ranks=ranks, special_tokens=special)
+    o = _oracle(ranks, special, pat)
+    text, off = corpus.config3(nbytes=288 << 20, seed=77)
+    d_text = torch.from_numpy(text).cuda()
+    d_off = torch.from_numpy(off.astype(np.int64)).cuda()
+    d_tok = torch.empty(len(text), dtype=torch.int32, device="cuda")
+    d_toff = torch.empty(len(off), dtype=torch.int64, device="cuda")
+    n = e._core_bpe.encode_device(d_text.data_ptr(), len(text), d_off.data_ptr(), len(off) - 1, d_tok.data_ptr(),
+                                  d_toff.data_ptr())
+    exp_t, exp_o = o.encode_ordinary_batch_np(text, off, CORES)
+    assert n == len(exp_t)
+    assert np.array_equal(d_toff.cpu().numpy().astype(np.uint64), exp_o)
+    assert np.array_equal(d_tok[:n].cpu().numpy().view(np.uint32), exp_t)
+    # and the host path on the same input agrees with it (three pipeline slots, default chunks)
+    assert _same(e.encode_ordinary_packed(text, off), exp_t, exp_o)
+
+
+def _adversarial_vocab(rnd, alpha, n_tokens, lens):
+    ranks = {bytes([i]): i for i in range(256)}
+    toks = set()
+    while len(toks) < n_tokens:
+        toks.add("".join(rnd.choice(alpha) for _ in range(rnd.choice(lens))).encode())
+    for t, r in zip(sorted(toks), rnd.sample(range(256, 256 + 4 * n_tokens), len(toks))):
+        ranks[t] = r                                          # random ranks: ties impossible, order adversarial
+    return ranks
+
+
+@pytest.mark.parametrize("trial", range(4))
+def test_giant_pieces_with_adversarial_vocabulary(trial):
+    """Pieces beyond 4 096 bytes (block per piece) and beyond 32 768 bytes (thread-block cluster per piece) on
+    vocabularies where a merge often creates a LOWER-ranked pair next to it (the "violation" of the
+    round-synchronous merge) and long chains of equal-rank candidates overlap."""
+    import tiktoken_b200
+    rnd = random.Random(1000 + trial)
+    alpha = ["ab", "abc", "ab", "abcd"][trial]
+    ranks = _adversarial_vocab(rnd, alpha, [12, 40, 25, 80][trial], [2, 2, 2, 3, 3, 4, 5, 6, 9, 14])
+    if trial == 2:                                            # powers of one letter: the x*1_000_000 shape, with gaps
+        for k, r in ((2, 300), (4, 290), (8, 310), (16, 280), (3, 305)):
+            ranks[b"a" * k] = 5000 + r
+    e = tiktoken_b200.Encoding("adv_giant", pat_str=vu.CL100K_PAT, mergeable_ranks=ranks, special_tokens={})
+    o = _oracle(ranks, {}, vu.CL100K_PAT)
+    pieces = []
+    for n in (4097, 5000, 10_000, 32_768, 32_769, 50_000, 100_000):
+        style = rnd.choice(["random", "periodic", "runs"])
+        if style == "random":
+            p = "".join(rnd.choice(alpha) for _ in range(n))
+        elif style == "periodic":
+            unit = "".join(rnd.choice(alpha) for _ in range(rnd.choice([1, 2, 3, 5, 7])))
+            p = (unit * (n // len(unit) + 1))[:n]
+        else:
+            p, out = "", []
+            while len(p) < n:
+                p += rnd.choice(alpha) * rnd.choice([1, 2, 3, 17, 64, 1000])
+            p = p[:n]
+        pieces.append(p)
+    for p in pieces:                                         # single-piece entry point (py.rs:145-150)
+        assert e._encode_single_piece(p) == o.encode_single_piece(p.encode()), len(p)
+    docs = [" ".join(pieces), pieces[3], "\n".join(pieces[::2]) + "\n", ""]     # letter runs split at the separators
+    assert e.encode_ordinary_batch(docs) == [o.encode_ordinary(d) for d in docs]
+
+
+def test_results_outlive_their_encoding():
+    import tiktoken_b200
+    pat, ranks, special, _ = vu.load_encoding("r50k_base", allow_real=False)
+    o = _oracle(ranks, special, pat)
+    text, off = corpus.config2(nbytes=1 << 20, seed=8)
+    exp_t, exp_o = o.encode_ordinary_batch_np(text, off, CORES)
+
+    def make():
+        return tiktoken_b200.Encoding("short_lived", pat_str=pat, mergeable_ranks=ranks, special_tokens=special)
+
+    toks = make().encode_ordinary_packed(text, off).tokens()     # Encoding and TokenBuffer both unreferenced now
+    gc.collect()
+    other = make()
+    junk = other.encode_ordinary_packed(text[::-1].copy() & 0x7F, np.asarray([0, len(text)], np.uint64))   # would reuse a pooled block
+    assert np.array_equal(toks, exp_t)
+    junk.close()
+    buf = make().encode_ordinary_packed(text, off)               # buffer alive, engine object gone
+    gc.collect()
+    assert np.array_equal(buf.offsets(), exp_o) and np.array_equal(buf.tokens(), exp_t)
+    buf.close()
+    buf.close()                                                  # idempotent
+
+
+def test_reference_host_class_runs_on_the_b200_core(monkeypatch):
+    """The drop-in itself: the reference's unmodified `tiktoken.core.Encoding` (installed wheel == the
+    reference's host code) with `tiktoken.core._tiktoken` swapped for `tiktoken_b200._tiktoken`
+    (core.py:7 import, :57 constructor, :161 encode_to_tiktoken_buffer -> np.frombuffer, :409-428 pickling)."""
+    tiktoken = pytest.importorskip("tiktoken")
+    import tiktoken.core as ref_core
+    from tiktoken_b200 import _tiktoken as shim
+    monkeypatch.setattr(ref_core, "_tiktoken", shim)
+    pat, ranks, special, _ = vu.load_encoding("cl100k_base", allow_real=False)
+    enc = tiktoken.Encoding("dropin", pat_str=pat, mergeable_ranks=ranks, special_tokens=special)
+    assert isinstance(enc._core_bpe, shim.CoreBPE)
+    o = _oracle(ranks, special, pat)
+    docs = ["hello world", "", "don't  stop\n\n  x", "日本語 text <|endoftext|> tail", "x" * 300, " " * 40 + "\n" * 3]
+    docs += [corpus.generate(corpus.ENGLISH, 5, 20_000).tobytes().decode()]
+    for d in docs:
+        assert enc.encode_ordinary(d) == o.encode_ordinary(d)
+        assert enc.encode(d, allowed_special="all") == o.encode(d, set(special))
+        assert enc.encode_to_numpy(d, allowed_special="all").tolist() == o.encode(d, set(special))
+        assert enc.decode(enc.encode(d, allowed_special="all")) == d
+    with pytest.raises(ValueError):
+        enc.encode("a <|endoftext|> b")                              # disallowed by default (core.py:120-124)
+    assert enc.encode_ordinary_batch(docs) == [o.encode_ordinary(d) for d in docs]          # thread pool over per-doc calls
+    assert enc.encode_batch(docs, allowed_special="all") == [o.encode(d, set(special)) for d in docs]
+    assert enc.decode_batch(enc.encode_ordinary_batch(docs)) == docs
+    assert enc.encode_single_token(b"a") == ranks[b"a"] and enc.decode_single_token_bytes(ranks[b"a"]) == b"a"
+    assert enc.decode_bytes(enc.encode_ordinary("héllo")) == "héllo".encode()
+    assert enc._encode_single_piece(b"helloqqqq") == o.encode_single_piece(b"helloqqqq")
+    assert sorted(enc.token_byte_values()) == sorted(ranks)
+    assert enc.encode_ordinary("\ud83d") == enc.encode_ordinary("�")                   # surrogate fix-up, core.py:77-80
+    enc2 = pickle.loads(pickle.dumps(enc))                                                 # by value (not in the registry)
+    assert isinstance(enc2._core_bpe, shim.CoreBPE)
+    assert enc2.encode_ordinary("pickled hello") == o.encode_ordinary("pickled hello")

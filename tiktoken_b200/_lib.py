@@ -80,6 +80,8 @@ def lib() -> C.CDLL:
     L.b200bpe_last_timings.argtypes = [vp, vp, C.POINTER(u32)]
     L.b200bpe_table_bytes.restype = i32
     L.b200bpe_table_bytes.argtypes = [vp, vp]
+    L.b200bpe_device_count.restype = i32
+    L.b200bpe_device_count.argtypes = []
     L.b200bpe_last_error.restype = C.c_char_p
     L.b200bpe_version.restype = C.c_char_p
     _lib = L
@@ -91,7 +93,7 @@ EXPORTS = [
     "b200bpe_encode_device", "b200bpe_encode_single_piece", "b200bpe_result_tokens",
     "b200bpe_result_offsets", "b200bpe_result_n_tokens", "b200bpe_result_n_docs", "b200bpe_result_free",
     "b200bpe_decode_bytes", "b200bpe_decode_batch", "b200bpe_last_timings", "b200bpe_table_bytes", "b200bpe_last_error",
-    "b200bpe_version",
+    "b200bpe_version", "b200bpe_device_count",
 ]
 
 

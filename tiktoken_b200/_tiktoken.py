@@ -34,33 +34,50 @@ def _flatten_bytes(items: list[bytes]):
     return arr, off
 
 
-class TokenBuffer:
-    """Owns one native result; exposes tokens / offsets without copying
-    (the role of TiktokenBuffer, src/py.rs:186-249)."""
+class _NativeView:
+    """Exposes native memory through the array interface and keeps its TokenBuffer alive for as long as
+    any ndarray built on it exists (np.asarray(view).base is this object)."""
 
-    def __init__(self, L, handle):
-        self._L, self._h = L, handle
+    def __init__(self, owner, ptr: int, n: int, typestr: str):
+        self._owner = owner
+        self.__array_interface__ = {"data": (ptr, True), "shape": (n,), "typestr": typestr, "version": 3}
+
+
+class TokenBuffer:
+    """Owns one native result; exposes tokens / offsets without copying (the role of TiktokenBuffer,
+    src/py.rs:186-249).  Lifetime: the buffer holds its CoreBPE, and every array handed out holds the buffer,
+    so neither `enc.encode_ordinary_packed(t, o).tokens()` nor dropping the Encoding first can dangle (the
+    native handle is reference-counted as well: b200bpe_destroy defers to the last b200bpe_result_free).
+    `close()` frees the native memory NOW: arrays obtained before it must not be used afterwards."""
+
+    def __init__(self, L, handle, owner=None):
+        self._L, self._h, self._owner = L, handle, owner
         self.n_tokens = int(L.b200bpe_result_n_tokens(handle))
         self.n_docs = int(L.b200bpe_result_n_docs(handle))
 
     def tokens(self) -> np.ndarray:
-        if self.n_tokens == 0:
+        if self.n_tokens == 0 or not self._h:
             return np.zeros(0, np.uint32)
         p = self._L.b200bpe_result_tokens(self._h)
-        a = np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_uint32)), shape=(self.n_tokens,))
-        a.flags.writeable = False
-        return a
+        return np.asarray(_NativeView(self, int(p), self.n_tokens, "<u4"))
 
     def offsets(self) -> np.ndarray:
+        if not self._h:
+            raise ValueError("TokenBuffer is closed")
         p = self._L.b200bpe_result_offsets(self._h)
-        a = np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_uint64)), shape=(self.n_docs + 1,))
-        a.flags.writeable = False
-        return a
+        return np.asarray(_NativeView(self, int(p), self.n_docs + 1, "<u8"))
 
     def close(self):
         if self._h:
             self._L.b200bpe_result_free(self._h)
             self._h = None
+        self._owner = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
 
     def __del__(self):
         self.close()
@@ -139,7 +156,7 @@ class CoreBPE:
         rc = self._L.b200bpe_encode_ordinary_batch(self._h, _ptr(text), _ptr(doc_off), len(doc_off) - 1,
                                                    C.byref(res))
         _lib.check(rc)
-        return TokenBuffer(self._L, res)
+        return TokenBuffer(self._L, res, self)
 
     def encode_batch_buffer(self, text: np.ndarray, doc_off: np.ndarray, allowed_special) -> TokenBuffer:
         allowed = np.asarray([1 if s in allowed_special else 0 for s in self._special_names] + [0], np.uint8)
@@ -147,7 +164,7 @@ class CoreBPE:
         rc = self._L.b200bpe_encode_batch(self._h, _ptr(text), _ptr(doc_off), len(doc_off) - 1, _ptr(allowed),
                                           C.byref(res))
         _lib.check(rc)
-        return TokenBuffer(self._L, res)
+        return TokenBuffer(self._L, res, self)
 
     @staticmethod
     def _pack(texts: list[str]):
@@ -201,7 +218,7 @@ class CoreBPE:
         a = np.frombuffer(piece, dtype=np.uint8)
         res = C.c_void_p()
         _lib.check(self._L.b200bpe_encode_single_piece(self._h, _ptr(a), len(piece), C.byref(res)))
-        buf = TokenBuffer(self._L, res)
+        buf = TokenBuffer(self._L, res, self)
         out = buf.tokens().tolist()
         buf.close()
         return out

@@ -1274,6 +1274,10 @@ struct b200bpe {
     size_t chunk_bytes = 64u << 20;
     std::mutex mu;
     std::vector<PinnedBuf> pinned_pool;
+    // results keep the engine alive: b200bpe_destroy with results outstanding only marks the handle dead, the last
+    // b200bpe_result_free tears it down (the reference's TiktokenBuffer owns its Vec, src/py.rs:186-189)
+    int live_results = 0;
+    bool dead = false;
 
     PinnedBuf take_pinned(size_t bytes) {
         for (size_t i = 0; i < pinned_pool.size(); i++)
@@ -1297,7 +1301,12 @@ static cudaError_t upload(Tp **dst, const void *src, size_t bytes) {
 }
 
 extern "C" const char *b200bpe_last_error(void) { return g_last_error.c_str(); }
-extern "C" const char *b200bpe_version(void) { return "b200bpe 0.1 (sm_100a)"; }
+extern "C" const char *b200bpe_version(void) { return "b200bpe 0.2 (sm_100a)"; }
+extern "C" int b200bpe_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
 
 extern "C" int b200bpe_create(const uint8_t *tok_bytes, const uint64_t *tok_off, const uint32_t *tok_rank,
                               uint32_t n_tok, const uint8_t *sp_bytes, const uint64_t *sp_off,
@@ -1375,14 +1384,26 @@ extern "C" int b200bpe_create(const uint8_t *tok_bytes, const uint64_t *tok_off,
     return B200BPE_OK;
 }
 
+static void engine_teardown(b200bpe *h);
+
 extern "C" void b200bpe_destroy(b200bpe_t *h) {
     if (!h) return;
+    {
+        std::lock_guard<std::mutex> lk(h->mu);
+        if (h->live_results > 0) { h->dead = true; return; }
+    }
+    engine_teardown(h);
+}
+
+static void engine_teardown(b200bpe *h) {
+    int prev = 0; cudaGetDevice(&prev);
     cudaSetDevice(h->device);
     cudaFree(h->d_byte_id); cudaFree(h->d_pair2); cudaFree(h->d_pair_tab); cudaFree(h->d_piece_tab);
     cudaFree(h->d_long_tab); cudaFree(h->d_long_blob); cudaFree(h->d_tok_boff); cudaFree(h->d_tok_blob); cudaFree(h->d_uc1); cudaFree(h->d_uc2); cudaFree(h->d_ascii);
     for (int i = 0; i < b200bpe::N_SLOTS; i++) h->slots[i].destroy();
     for (auto &b : h->pinned_pool) cudaFreeHost(b.p);
     delete h;
+    cudaSetDevice(prev);
 }
 
 // The device pipeline.  All pointers are device pointers on h->device; d_text must be 16-byte
@@ -1671,6 +1692,7 @@ static int encode_host(b200bpe *h, const uint8_t *text, const uint64_t *doc_off,
     }
     memcpy(h->last_ms, sum_ms, sizeof(sum_ms)); h->last_launches = launches;
     r->n_tokens = token_base;
+    h->live_results++;                                            // caller holds h->mu
     *out = r;
     return B200BPE_OK;
 }
@@ -1757,6 +1779,8 @@ extern "C" int b200bpe_encode_batch(b200bpe_t *h, const uint8_t *text, const uin
     }
     r->voff[n_docs] = r->vtok.size(); r->n_tokens = r->vtok.size();
     h->give_pinned(seg->tok); h->give_pinned(seg->off); delete seg;
+    h->live_results--;                                            // the internal segment result
+    h->live_results++;
     *out = r;
     return B200BPE_OK;
 }
@@ -1771,11 +1795,16 @@ extern "C" uint64_t b200bpe_result_n_tokens(const b200bpe_result_t *r) { return 
 extern "C" uint64_t b200bpe_result_n_docs(const b200bpe_result_t *r) { return r->n_docs; }
 extern "C" void b200bpe_result_free(b200bpe_result_t *r) {
     if (!r) return;
-    if (!r->on_host_vec && r->owner) {
-        std::lock_guard<std::mutex> lk(r->owner->mu);
-        r->owner->give_pinned(r->tok); r->owner->give_pinned(r->off);
+    b200bpe *h = r->owner;
+    bool last = false;
+    if (h) {
+        std::lock_guard<std::mutex> lk(h->mu);
+        if (!r->on_host_vec) { h->give_pinned(r->tok); h->give_pinned(r->off); }
+        h->live_results--;
+        last = h->dead && h->live_results == 0;
     }
     delete r;
+    if (last) engine_teardown(h);
 }
 
 extern "C" int b200bpe_decode_bytes(b200bpe_t *h, const uint32_t *tokens, uint64_t n_tokens, uint8_t *out,
@@ -1859,6 +1888,7 @@ extern "C" int b200bpe_decode_batch(b200bpe_t *h, const uint32_t *tokens, const 
     cudaEventElapsedTime(&h->last_ms[4], S.ev[1], S.ev[2]);
     cudaEventElapsedTime(&h->last_ms[6], S.ev[2], S.ev[3]);
     h->last_launches = 6;
+    h->live_results++;
     *out = r;
     return B200BPE_OK;
 }

@@ -62,12 +62,22 @@ B2_HD uint32_t pair_hash(uint32_t a, uint32_t b) {
     return h;
 }
 
-B2_HD uint64_t piece_hash(uint64_t k0, uint64_t k1, uint32_t len) {
-    uint64_t h = (k0 ^ ((uint64_t)len * 0xD6E8FEB86659FD93ull)) * 0x9E3779B97F4A7C15ull;
-    h ^= h >> 32;
-    h = (h ^ k1) * 0xC2B2AE3D27D4EB4Full;
-    h ^= h >> 29;
+// Hash of a piece of <= 16 bytes given as four little-endian words (zero padded) + its length: 32-bit
+// multiply-xorshift rounds (one IMAD per word), not a 64-bit mix -- the probe kernel hashes every piece of the
+// corpus, and 64-bit multiplies are four instructions each on the SM.
+B2_HD uint32_t piece_hash4(uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t len) {
+    uint32_t h = (a0 ^ (len * 0x9E3779B1u)) * 0x85EBCA6Bu;
+    h ^= h >> 13;
+    h = (h ^ a1) * 0xC2B2AE35u;
+    h ^= h >> 16;
+    h = (h ^ a2) * 0x27D4EB2Fu;
+    h ^= h >> 15;
+    h = (h ^ a3) * 0x165667B1u;
+    h ^= h >> 16;
     return h;
+}
+B2_HD uint32_t piece_hash(uint64_t k0, uint64_t k1, uint32_t len) {
+    return piece_hash4((uint32_t)k0, (uint32_t)(k0 >> 32), (uint32_t)k1, (uint32_t)(k1 >> 32), len);
 }
 
 // 64-bit hash of a byte string given as little-endian u64 words (last one zero padded):
