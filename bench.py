@@ -5,22 +5,31 @@ Mtokens/s, cl100k_base, 1 GiB synthetic English-like corpus = SURVEY.md 8(d) con
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload config2]
 
 A "step" = one pass of the hot path over one batch (the whole workload of this rank).
-  value    device-resident: text + doc offsets already in HBM, tokens + offsets left in HBM;
-           timed with CUDA events on the launching stream, max over ranks.
+  value    device-resident: text + doc offsets already in HBM, tokens + offsets left in HBM.  The K steps are
+           ENQUEUED back to back on one CUDA stream (b200bpe_encode_device_async: no host synchronisation inside a
+           step; the per-step count exchange is an NCCL all-gather enqueued behind the pipeline from a device buffer
+           the last kernel fills) and timed with CUDA events recorded on that stream; max over ranks.
   e2e      the same metric through the public host API (Encoding.encode_ordinary_packed ->
            C ABI b200bpe_encode_ordinary_batch) with pinned HOST buffers: H2D of the text, the
-           kernels and D2H of tokens + offsets are all inside the timed region.
-  roofline achieved algorithmic bytes/s of the dominant kernel (encode_tiles) from CUDA events
-           recorded by the engine around that launch, against the measured HBM peak.
+           kernels and D2H of tokens + offsets are all inside the timed region.  Its output is compared
+           byte for byte with the device-resident result on every rank.
+  api      the calls a tiktoken user makes: encode_ordinary_batch(list[str]) (Python marshalling + pageable memory
+           through the pinned staging ring) and encode_batch with the default disallowed_special="all" (device scan).
+  roofline achieved algorithmic bytes/s of the dominant kernel from CUDA events recorded by the engine around
+           that launch, against the measured HBM peak; and the same for the whole pipeline.
+  configs  every other BASELINE.json config at its stated size, same method, with a parity flag each.
+  strong   ONE 1 GiB corpus split over the ranks (BASELINE asks for "a 1 GB corpus at 1/2/4/8"), next to the weak line.
   cpu_baseline / --impl reference: the reference engine itself (the tiktoken wheel's Rust CoreBPE
            driven through tiktoken.Encoding.encode_ordinary_batch with all host cores) on a bounded
            sample of the same workload; if the wheel cannot be imported, the oracle port.
 N > 1 (torchrun, one rank per GPU): documents shard across ranks (weak scaling: every rank has its
 own corpus of the configured size); the only exchange is an NCCL all-gather of per-rank counts.
+Every rank is gated against the oracle before any number is reported.
 """
 from __future__ import annotations
 
 import argparse
+import hashlib
 import json
 import os
 import subprocess
@@ -39,13 +48,14 @@ import vocab_util as vu   # noqa: E402
 
 WORKLOADS = {
     # name: (encoding, builder, description)
+    "config1": ("r50k_base", lambda n, seed: corpus.config1(n, seed), "gpt2/r50k_base, ONE 1 MiB ASCII document (plumbing)"),
     "config2": ("cl100k_base", lambda n, seed: corpus.config2(n, seed), "cl100k_base, english-like, ~64 KiB docs"),
     "config3": ("o200k_base", lambda n, seed: corpus.config3(n, seed), "o200k_base, mixed UTF-8, docs 4-256 KiB"),
-    "config4": ("cl100k_base", lambda n, seed: corpus.config4(max(1, n // 100), seed), "cl100k_base, ~100 B docs"),
+    "config4": ("cl100k_base", lambda n, seed: corpus.config4(max(1, round(n / 102.0)), seed), "cl100k_base, ~100 B docs"),
     "config5": ("p50k_base", lambda n, seed: corpus.config5(n, seed), "p50k_base, one code-like document"),
 }
-DEFAULT_BYTES = {"config2": 1 << 30, "config3": 1 << 30, "config4": 1 << 30, "config5": 64 << 20}
-SEEDS = {"config2": 1002, "config3": 1003, "config4": 1004, "config5": 1005}
+DEFAULT_BYTES = {"config1": 1 << 20, "config2": 1 << 30, "config3": 1 << 30, "config4": 1_020_000_000, "config5": 64 << 20}
+SEEDS = {"config1": 1001, "config2": 1002, "config3": 1003, "config4": 1004, "config5": 1005}
 
 
 def measured_peak():
@@ -153,6 +163,122 @@ def cpu_reference_run(pat, ranks, special, text, off, target_s, cores):
                                            "sample": f"first {k} docs = {b} bytes of the workload, {dt:.1f} s"}
 
 
+class Bench:
+    """One workload on this rank: corpus, engine, device buffers, and the three measurements."""
+
+    def __init__(self, workload, nbytes, rank, world, local_rank, seed_offset=0, text_off=None):
+        import torch
+        import tiktoken_b200
+        self.torch = torch
+        self.workload, self.rank, self.world = workload, rank, world
+        enc_name, builder, self.desc = WORKLOADS[workload]
+        self.enc_name = enc_name
+        self.pat, self.ranks, self.special, self.vocab_src = vu.load_encoding(enc_name)
+        self.enc = tiktoken_b200.Encoding(f"{enc_name}_bench_{workload}", pat_str=self.pat, mergeable_ranks=self.ranks,
+                                          special_tokens=self.special, device=local_rank)
+        self.core = self.enc._core_bpe
+        if text_off is None:
+            text_off = builder(nbytes, SEEDS[workload] + seed_offset)
+        self.text, self.off = text_off
+        self.n_docs, self.N = len(self.off) - 1, len(self.text)
+        # pinned host copies (the e2e path copies FROM these every step)
+        self.h_text = torch.empty(max(self.N, 1), dtype=torch.uint8, pin_memory=True)
+        self.h_text.numpy()[:self.N] = self.text
+        self.h_off = torch.empty(self.n_docs + 1, dtype=torch.int64, pin_memory=True)
+        self.h_off.numpy()[:] = self.off.astype(np.int64)
+        self.stream = torch.cuda.Stream()                                       # a real (non-default) stream handle
+        with torch.cuda.stream(self.stream):
+            self.d_text = self.h_text.cuda(non_blocking=True)
+            self.d_off = self.h_off.cuda(non_blocking=True)
+            self.d_tok = torch.empty(max(self.N, 1), dtype=torch.int32, device="cuda")
+            self.d_toff = torch.empty(self.n_docs + 1, dtype=torch.int64, device="cuda")
+        self.stream.synchronize()
+
+    # ---- one device-resident step, enqueue only
+    def enqueue(self, counts_ptr=0):
+        self.core.encode_device_async(self.d_text.data_ptr(), self.N, self.d_off.data_ptr(), self.n_docs,
+                                      self.d_tok.data_ptr(), self.d_toff.data_ptr(), counts_ptr, self.stream.cuda_stream)
+
+    def step_sync(self):
+        self.enqueue()
+        return self.core.device_wait()
+
+    def parity(self, cores, sample_bytes=48 << 20):
+        """Bit-exact check of the device-resident result against the oracle on a sample of whole documents starting at
+        a rank-dependent place; the full result is then the reference for the e2e comparison."""
+        from oracle import Oracle
+        n_tok = self.step_sync()
+        orc = Oracle(self.ranks, self.special, self.pat)
+        off = self.off
+        if self.n_docs == 1 or self.N <= sample_bytes:
+            lo, hi = 0, self.n_docs
+            if self.n_docs == 1 and self.N > (8 << 20):
+                # one huge document: the oracle is single-threaded on it -- check a prefix cut at a line end as its own
+                # document on BOTH sides (exact for the prefix because the cut is made the document end for both)
+                cut = int(np.flatnonzero(self.text[:8 << 20] == 0x0A)[-1]) + 1
+                sub_off = np.asarray([0, cut], np.uint64)
+                buf = self.enc.encode_ordinary_packed(self.text[:cut], sub_off)
+                exp_t, exp_o = orc.encode_ordinary_batch_np(self.text[:cut], sub_off, 1)
+                ok = np.array_equal(buf.tokens(), exp_t) and np.array_equal(buf.offsets(), exp_o)
+                buf.close()
+                return ok, n_tok
+        else:
+            start = (self.rank * 0x9E3779B1 + 12345) % max(1, self.N - sample_bytes)
+            lo = int(np.searchsorted(off, start, side="left"))
+            hi = int(np.searchsorted(off, int(off[lo]) + sample_bytes, side="right")) - 1
+            hi = max(lo + 1, min(hi, self.n_docs))
+        b0, b1 = int(off[lo]), int(off[hi])
+        exp_t, exp_o = orc.encode_ordinary_batch_np(self.text[b0:b1], (off[lo:hi + 1] - off[lo]).astype(np.uint64), cores)
+        got_o = self.d_toff[lo:hi + 1].cpu().numpy().astype(np.uint64)
+        got_t = self.d_tok[int(got_o[0]):int(got_o[-1])].cpu().numpy().view(np.uint32)
+        ok = np.array_equal(got_o - got_o[0], exp_o) and np.array_equal(got_t, exp_t)
+        return ok, n_tok
+
+    def e2e(self, steps, compare=True):
+        """Host pinned -> host pinned through the public API; returns (seconds per step, tokens, identical to the
+        device-resident result?)."""
+        torch = self.torch
+        h_text_np, h_off_np = self.h_text.numpy()[:self.N], self.h_off.numpy().view(np.uint64)
+        for _ in range(2):
+            self.enc.encode_ordinary_packed(h_text_np, h_off_np).close()
+        torch.cuda.synchronize()
+        ts, same, ntok = [], True, 0
+        for i in range(steps):
+            t0 = time.perf_counter()
+            buf = self.enc.encode_ordinary_packed(h_text_np, h_off_np)      # H2D + kernels + D2H, synchronous
+            ts.append(time.perf_counter() - t0)
+            ntok = buf.n_tokens
+            if compare and i == 0:
+                dev_t = self.d_tok[:ntok].cpu().numpy().view(np.uint32)
+                dev_o = self.d_toff.cpu().numpy().astype(np.uint64)
+                same = bool(np.array_equal(buf.tokens(), dev_t) and np.array_equal(buf.offsets(), dev_o))
+            buf.close()
+        return float(np.mean(ts)), ntok, same, self.core.last_timings()
+
+    def close(self):
+        del self.d_text, self.d_off, self.d_tok, self.d_toff, self.h_text, self.h_off, self.core, self.enc
+        self.torch.cuda.empty_cache()
+
+
+def timed_device_loop(b: Bench, steps, world, xchg):
+    """K steps enqueued back to back on b.stream, one NCCL count exchange per step enqueued behind each pipeline;
+    CUDA events on that stream; returns ms for the K steps (this rank)."""
+    torch = b.torch
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with torch.cuda.stream(b.stream):
+        ev0.record(b.stream)
+        for _ in range(steps):
+            b.enqueue(xchg.send_ptr())
+            xchg.post_device()             # all-gather of (tokens, docs) from the device buffer the pipeline just filled
+            if len(xchg._pending) >= xchg.depth - 1:
+                xchg.wait()
+        placements = xchg.drain()          # every exchange completes inside the timed region
+        ev1.record(b.stream)
+    n_tok = b.core.device_wait()
+    b.stream.synchronize()
+    return ev0.elapsed_time(ev1), n_tok, placements
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -163,6 +289,8 @@ def main():
     ap.add_argument("--bytes", type=int, default=0, help="override the per-rank corpus size (development)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="skip the block with the other BASELINE configs")
+    ap.add_argument("--no-extras", action="store_true", help="skip api / strong-scaling / one-process multi-GPU lines")
     ap.add_argument("--decode", action="store_true", help="also time the device decode of the produced tokens (next row)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
@@ -172,18 +300,21 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     enc_name, builder, wl_desc = WORKLOADS[args.workload]
     nbytes = args.bytes or DEFAULT_BYTES[args.workload]
-    pat, ranks, special, vocab_src = vu.load_encoding(enc_name)
     cores = os.cpu_count() or 1
-    config = {"workload": f"{args.workload}: {wl_desc}", "bytes_per_gpu": nbytes, "encoding": enc_name,
-              "vocab": f"{vocab_src} ({len(ranks)} mergeable ranks)", "seed": SEEDS[args.workload],
-              "l2": "inputs (>= 64 MiB text per step, streamed once) exceed or equal the 126 MB L2; no reuse between steps",
-              "parallelism": f"doc-sharded x{world}"}
+
+    def config_of(workload, nb, parallelism=None):
+        e, _, d = WORKLOADS[workload]
+        return {"workload": f"{workload}: {d}", "bytes_per_gpu": nb, "encoding": e, "seed": SEEDS[workload],
+                "l2": "inputs (>= 64 MiB text per step, streamed once) exceed or equal the 126 MB L2; no reuse between steps",
+                "parallelism": parallelism or f"doc-sharded x{world}"}
 
     # ---------------------------------------------------------------- reference arm (CPU)
     if args.impl == "reference":
         if rank != 0:
             return 0
-        text, off = builder(min(nbytes, 256 << 20), SEEDS[args.workload])
+        pat, ranks, special, vocab_src = vu.load_encoding(enc_name)
+        sample_cap = min(nbytes, 256 << 20)
+        text, off = builder(sample_cap, SEEDS[args.workload])
         vals, toks, secs = [], [], []
         desc = None
         for i in range(args.warmup + args.steps):
@@ -191,6 +322,9 @@ def main():
             if i >= args.warmup:
                 vals.append(gbs); toks.append(mts); secs.append(desc["seconds"])
         v = float(np.mean(vals))
+        config = config_of(args.workload, nbytes)
+        config["vocab"] = f"{vocab_src} ({len(ranks)} mergeable ranks)"
+        config["timed_sample"] = f"each step times a bounded prefix of the first {sample_cap} bytes of the workload (see cpu_baseline.sample); a rate"
         line = {"impl": "reference", "metric": "input_GB_per_s", "value": v, "unit": "GB/s", "n_gpus": args.gpus,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": float(np.mean(secs)) * 1e3, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
@@ -207,167 +341,266 @@ def main():
         print(json.dumps({"error": "no CUDA device: tiktoken_b200 has no CPU fallback"}))
         return 2
     torch.cuda.set_device(local_rank)
+    from tiktoken_b200.sharding import CountExchange, bind_to_gpu_numa
+    numa = bind_to_gpu_numa(local_rank)          # before any pinned allocation: first touch on the GPU's node
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    import tiktoken_b200
-    from tiktoken_b200.sharding import CountExchange, gather_counts
-
-    enc = tiktoken_b200.Encoding(enc_name + "_bench", pat_str=pat, mergeable_ranks=ranks, special_tokens=special,
-                                 device=local_rank)
-    core = enc._core_bpe
-    text, off = builder(nbytes, SEEDS[args.workload] + 7919 * rank)        # weak scaling: own corpus per rank
-    n_docs = len(off) - 1
-    N = len(text)
-
-    # pinned host copies (the e2e path copies FROM these every step)
-    h_text = torch.empty(N, dtype=torch.uint8, pin_memory=True)
-    h_text.numpy()[:] = text
-    h_off = torch.empty(n_docs + 1, dtype=torch.int64, pin_memory=True)
-    h_off.numpy()[:] = off.astype(np.int64)
-    # device-resident inputs / outputs for `value`
-    d_text = h_text.cuda(non_blocking=True)
-    d_off = h_off.cuda(non_blocking=True)
-    d_tok = torch.empty(N, dtype=torch.int32, device="cuda")
-    d_toff = torch.empty(n_docs + 1, dtype=torch.int64, device="cuda")
-    torch.cuda.synchronize()
-    stream = torch.cuda.current_stream()
-
-    def step_device():
-        return core.encode_device(d_text.data_ptr(), N, d_off.data_ptr(), n_docs, d_tok.data_ptr(), d_toff.data_ptr(),
-                                  stream.cuda_stream)
-
-    # ---- parity gate on a sample before any number is reported
-    n_tok = step_device()
-    if rank == 0:
-        from oracle import Oracle
-        orc = Oracle(ranks, special, pat)
-        k = int(min(n_docs, max(1, np.searchsorted(off, 6 << 20))))
-        exp_t, exp_o = orc.encode_ordinary_batch_np(text[:int(off[k])], off[:k + 1], cores)
-        got_o = d_toff[:k + 1].cpu().numpy().astype(np.uint64)
-        got_t = d_tok[:int(got_o[-1])].cpu().numpy().view(np.uint32)
-        if not (np.array_equal(got_o, exp_o) and np.array_equal(got_t, exp_t)):
-            print(json.dumps({"error": "PARITY FAILURE against the oracle on the bench workload"}))
-            return 3
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- value: device-resident, CUDA events on the launching stream
-    for _ in range(args.warmup):
-        gather_counts(step_device(), n_docs, rank, world, device="cuda")     # also warms the NCCL communicator
-    sampler = ClockSampler(local_rank)
-    barrier()
-    sampler.start()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    stage = {"pretok_ms": [], "encode_ms": [], "probe_ms": [], "gather_ms": [], "long_ms": [], "mark_docs_ms": [], "device_total_ms": []}
-    launches = 0
-    ev0.record(stream)
-    xchg = CountExchange(rank, world, device="cuda")
-    for _ in range(args.steps):
-        n_tok = step_device()
-        xchg.post(n_tok, n_docs)           # NCCL all-gather of (tokens, docs), next to the following step's kernels
-        tm = core.last_timings()
-        for key in stage:
-            stage[key].append(tm[key])
-        launches += tm["launches"]
-    placements = xchg.drain()              # every exchange completes inside the timed region
-    counts = placements[-1][0]
-    ev1.record(stream)
-    barrier()
-    clocks = sampler.stop()
-    ms_total = ev0.elapsed_time(ev1)
-    t = torch.tensor([ms_total], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_step = float(t.item()) / args.steps
-    tot = torch.tensor([N, n_tok], dtype=torch.int64, device="cuda")
-    if world > 1:
-        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
-    tot_bytes, tot_tokens = int(tot[0].item()), int(tot[1].item())
-    value = tot_bytes / (ms_step * 1e-3) / 1e9
-
-    # ---- e2e: host buffers through the public API, copies inside the timed region
-    h_text_np, h_off_np = h_text.numpy(), h_off.numpy().view(np.uint64)
-    for _ in range(2):
-        enc.encode_ordinary_packed(h_text_np, h_off_np).close()
-    barrier()
-    e2e_t = []
-    for _ in range(args.steps):
-        t0 = time.perf_counter()
-        buf = enc.encode_ordinary_packed(h_text_np, h_off_np)      # H2D + kernels + D2H, synchronous
-        e2e_t.append(time.perf_counter() - t0)
-        e2e_tokens = buf.n_tokens
-        buf.close()
-    barrier()
-    t2 = torch.tensor([float(np.mean(e2e_t))], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t2, op=dist.ReduceOp.MAX)
-    e2e_value = tot_bytes / float(t2.item()) / 1e9
-    e2e_tm = core.last_timings()
-
-    if rank != 0:
+    def allmax(x):
+        t = torch.tensor([float(x)], dtype=torch.float64, device="cuda")
         if world > 1:
-            dist.destroy_process_group()
-        return 0
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
 
-    # ---- roofline of the dominant kernel (probe_kernel), algorithmic bytes per launch
+    def allsum(*xs):
+        t = torch.tensor([int(x) for x in xs], dtype=torch.int64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return [int(v) for v in t.tolist()]
+
+    def allok(flag):
+        t = torch.tensor([0 if flag else 1], dtype=torch.int64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return int(t.item()) == 0
+
+    def measure(b: Bench, steps, warmup, sample_clocks=False):
+        """parity gate (every rank) -> value -> e2e (compared with the device result); returns a dict."""
+        ok, n_tok = b.parity(cores)
+        if not allok(ok):
+            return {"parity": False, "error": "PARITY FAILURE against the oracle"}
+        xchg = CountExchange(rank, world, device="cuda")
+        for _ in range(warmup):
+            timed_device_loop(b, 1, world, xchg)                # also warms the NCCL communicator and settles work-space sizes
+        sampler = ClockSampler(local_rank) if (sample_clocks and rank == 0) else None
+        barrier()
+        if sampler:
+            sampler.start()
+        ms_total, n_tok, placements = timed_device_loop(b, steps, world, xchg)
+        barrier()
+        clocks = sampler.stop() if sampler else None
+        ms_step = allmax(ms_total) / steps
+        tot_bytes, tot_tokens = allsum(b.N, n_tok)
+        b.step_sync()                                           # one instrumented step for the per-stage events
+        tm = b.core.last_timings()
+        e2e_s, e2e_tokens, same, e2e_tm = b.e2e(steps)
+        barrier()
+        e2e_s = allmax(e2e_s)
+        same = allok(same and e2e_tokens == n_tok)
+        return {"parity": bool(same), "value": tot_bytes / (ms_step * 1e-3) / 1e9, "ms_per_step": ms_step,
+                "mtokens_per_s": tot_tokens / (ms_step * 1e-3) / 1e6, "bytes": tot_bytes, "tokens": tot_tokens,
+                "n_tok_rank": n_tok, "stage_ms": {k: v for k, v in tm.items() if k.endswith("_ms")}, "launches": tm["launches"],
+                "e2e": {"value": tot_bytes / e2e_s / 1e9, "unit": "GB/s", "h2d_bytes_per_step": int(b.N + 8 * (b.n_docs + 1)),
+                        "d2h_bytes_per_step": int(4 * e2e_tokens + 8 * (b.n_docs + 1)), "ms_per_step": e2e_s * 1e3,
+                        "mtokens_per_s": tot_tokens / e2e_s / 1e6, "identical_to_device_result": bool(same),
+                        "h2d_ms": e2e_tm["h2d_ms"], "d2h_ms": e2e_tm["d2h_ms"], "device_ms": e2e_tm["device_total_ms"]},
+                "clocks": clocks, "counts_exchanged": [int(x) for x in placements[-1][0][:, 0]] if placements else None}
+
+    b = Bench(args.workload, nbytes, rank, world, local_rank, seed_offset=7919 * rank)   # weak scaling: own corpus per rank
+    m = measure(b, args.steps, args.warmup, sample_clocks=True)
+    if not m.get("parity"):
+        if rank == 0:
+            print(json.dumps({"error": m.get("error", "e2e result differs from the device-resident result"), "detail": m}))
+        return 3
+    N, n_tok, n_docs = b.N, m["n_tok_rank"], b.n_docs
+    stage = m["stage_ms"]
+    config = config_of(args.workload, nbytes)
+    config["vocab"] = f"{b.vocab_src} ({len(b.ranks)} mergeable ranks)"
+    config["numa"] = numa
+
+    # ---- roofline of the dominant kernel, algorithmic bytes per launch (DESIGN.md 3)
     peak, peak_src = measured_peak()
-    probe_ms = float(np.mean(stage["probe_ms"]))
-    enc_ms = float(np.mean(stage["encode_ms"]))
-    alg_probe = N + N // 8 + 4 * n_tok                      # text + piece bitmask read, one 4-byte slot per piece written
-    achieved = alg_probe / (probe_ms * 1e-3) / 1e9
+    kern_ms = {"pretok_kernel": stage["pretok_ms"], "probe_kernel": stage["probe_ms"],
+               "miss_sort+miss_kernel": stage["encode_ms"] - stage["probe_ms"], "scan+gather_kernel": stage["gather_ms"],
+               "long-piece kernels": stage["long_ms"]}
+    alg = {"pretok_kernel": N + N // 8 + N // 8,                      # text + doc mask read, piece mask written
+           "probe_kernel": N + N // 8 + 4 * n_tok,                    # text + piece mask read, one 4-byte slot per piece written
+           "miss_sort+miss_kernel": None, "scan+gather_kernel": 8 * n_tok + 8 * (n_docs + 1),   # slots read, tokens + doc offsets written
+           "long-piece kernels": None}
+    dominant = max((k for k in kern_ms if alg[k]), key=lambda k: kern_ms[k])
+    achieved = alg[dominant] / (kern_ms[dominant] * 1e-3) / 1e9
     traffic = None
     prof = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     if os.path.exists(prof):
         try:
-            traffic = json.load(open(prof)).get("probe_kernel", {}).get("dram_bytes_per_launch")
+            traffic = json.load(open(prof)).get(dominant.split("+")[-1], {}).get("dram_bytes_per_launch")
         except Exception:
             traffic = None
-    pre_ms = float(np.mean(stage["pretok_ms"]))
-    pipeline_alg = N + 4 * n_tok + 16 * (n_docs + 1)
-    dev_ms = float(np.mean(stage["device_total_ms"]))
+    pipeline_alg = N + 4 * n_tok + 16 * (n_docs + 1)                    # SURVEY 8(d): text + tokens + both offset arrays
+    dev_ms = stage["device_total_ms"]
     line = {
-        "metric": "input_GB_per_s", "value": value, "unit": "GB/s", "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+        "metric": "input_GB_per_s", "value": m["value"], "unit": "GB/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": m["ms_per_step"], "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u8", "data": "synthetic", "config": config,
-        "mtokens_per_s": tot_tokens / (ms_step * 1e-3) / 1e6, "bytes_per_token": tot_bytes / max(1, tot_tokens),
-        "n_docs_per_gpu": n_docs, "gpu_launches": launches,
-        "stage_ms": {k: float(np.mean(v)) for k, v in stage.items()},
-        "roofline": {"bound": "hbm", "kernel": "probe_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+        "mtokens_per_s": m["mtokens_per_s"], "bytes_per_token": m["bytes"] / max(1, m["tokens"]),
+        "n_docs_per_gpu": n_docs, "gpu_launches": m["launches"] * args.steps,
+        "timing": "K async steps on one CUDA stream, events on that stream, no host sync inside a step; max over ranks",
+        "parity": {"oracle_sample_every_rank": True, "e2e_identical_to_device_result": True},
+        "stage_ms": stage, "kernel_ms": kern_ms,
+        "roofline": {"bound": "hbm", "kernel": dominant, "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                     "algorithmic_bytes_per_launch": alg_probe, "kernel_ms": probe_ms,
-                     "encode_stage": {"kernels": "probe + miss sort + miss merge", "ms": enc_ms,
-                                      "achieved": (N + N // 8 + 4 * n_tok) / (enc_ms * 1e-3) / 1e9},
-                     "pretok_kernel": {"achieved": (N + N // 8 + N // 8) / (pre_ms * 1e-3) / 1e9, "kernel_ms": pre_ms,
-                                       "frac": (N + N // 4) / (pre_ms * 1e-3) / 1e9 / peak},
-                     "pipeline": {"achieved": pipeline_alg / (dev_ms * 1e-3) / 1e9,
+                     "algorithmic_bytes_per_launch": alg[dominant], "kernel_ms": kern_ms[dominant],
+                     "per_kernel": {k: {"ms": kern_ms[k], "algorithmic_bytes": alg[k],
+                                        "frac": (alg[k] / (kern_ms[k] * 1e-3) / 1e9 / peak) if alg[k] and kern_ms[k] > 0 else None}
+                                    for k in kern_ms},
+                     "pipeline": {"algorithmic_bytes": pipeline_alg, "achieved": pipeline_alg / (dev_ms * 1e-3) / 1e9,
                                   "frac": pipeline_alg / (dev_ms * 1e-3) / 1e9 / peak,
                                   "hbm_read_only_frac": N / (dev_ms * 1e-3) / 1e9 / peak, "device_ms": dev_ms}},
-        "e2e": {"value": e2e_value, "unit": "GB/s", "h2d_bytes_per_step": int(N + 8 * (n_docs + 1)),
-                "d2h_bytes_per_step": int(4 * e2e_tokens + 8 * (n_docs + 1)), "ms_per_step": float(t2.item()) * 1e3,
-                "mtokens_per_s": tot_tokens / float(t2.item()) / 1e6,
-                "h2d_ms": e2e_tm["h2d_ms"], "d2h_ms": e2e_tm["d2h_ms"], "device_ms": e2e_tm["device_total_ms"]},
-        "clocks": clocks,
+        "e2e": m["e2e"], "clocks": m["clocks"],
     }
+
+    # ---- the calls a tiktoken user makes (host marshalling inside the timed region), rank 0 only
+    if not args.no_extras and args.workload == "config2":
+        barrier()
+        if rank == 0:
+            try:
+                api = {}
+                k = int(np.searchsorted(b.off, min(N, 256 << 20), side="right")) - 1
+                nb = int(b.off[k])
+                pageable = np.array(b.text[:nb])                            # ordinary (pageable) numpy memory
+                poff = b.off[:k + 1].astype(np.uint64)
+                for _ in range(2):
+                    b.enc.encode_ordinary_packed(pageable, poff).close()     # warm: staging blocks, pinned result of this size
+                t0 = time.perf_counter()
+                buf = b.enc.encode_ordinary_packed(pageable, poff); dt = time.perf_counter() - t0
+                buf.close()
+                api["packed_pageable"] = {"value": nb / dt / 1e9, "unit": "GB/s", "bytes": nb,
+                                          "what": "encode_ordinary_packed(numpy in pageable memory): pinned staging ring + H2D + kernels + D2H"}
+                b.enc.encode_packed(b.h_text.numpy()[:nb], poff, allowed_special={"<|endoftext|>"}).close()
+                t0 = time.perf_counter()
+                buf = b.enc.encode_packed(b.h_text.numpy()[:nb], poff, allowed_special={"<|endoftext|>"}); dt = time.perf_counter() - t0
+                buf.close()
+                api["encode_batch_default_policy_pinned"] = {
+                    "value": nb / dt / 1e9, "unit": "GB/s", "bytes": nb,
+                    "what": "encode_batch semantics (allowed {<|endoftext|>}, every other special disallowed = default policy) "
+                            "on packed pinned input: device multi-pattern scan + pipeline, zero-copy pinned result"}
+                docs = [bytes(b.text[int(b.off[i]):int(b.off[i + 1])]).decode("utf-8") for i in range(min(k, 1024))]
+                dbytes = sum(len(d.encode()) for d in docs)
+                b.enc.encode_ordinary_batch(docs)
+                t0 = time.perf_counter()
+                out = b.enc.encode_ordinary_batch(docs); dt = time.perf_counter() - t0
+                api["list_str_to_list_list_int"] = {"value": dbytes / dt / 1e9, "unit": "GB/s", "bytes": dbytes, "docs": len(docs),
+                                                    "what": "encode_ordinary_batch(list[str]) -> list[list[int]]: C marshalling both ways + device"}
+                t0 = time.perf_counter()
+                toks, offs = b.enc.encode_ordinary_batch_to_numpy(docs); dt = time.perf_counter() - t0
+                api["list_str_to_numpy"] = {"value": dbytes / dt / 1e9, "unit": "GB/s", "bytes": dbytes,
+                                            "what": "encode_ordinary_batch_to_numpy(list[str]) -> (tokens, offsets) arrays"}
+                del out, toks, offs, docs, pageable
+                line["api"] = api
+            except Exception as e:                                   # noqa: BLE001
+                line["api"] = {"error": repr(e)}
+        barrier()
+
     if args.decode and world == 1:
-        buf = enc.encode_ordinary_packed(h_text_np, h_off_np)
+        h_text_np, h_off_np = b.h_text.numpy()[:N], b.h_off.numpy().view(np.uint64)
+        buf = b.enc.encode_ordinary_packed(h_text_np, h_off_np)
         dtoks, doffs = np.array(buf.tokens()), np.array(buf.offsets())
         buf.close()
-        enc.decode_packed(dtoks, doffs)
+        b.enc.decode_packed(dtoks, doffs)
         dt = []
         for _ in range(3):
             t0 = time.perf_counter()
-            data, boff = enc.decode_packed(dtoks, doffs)
+            data, boff = b.enc.decode_packed(dtoks, doffs)
             dt.append(time.perf_counter() - t0)
         assert len(data) == N
         line["decode"] = {"value": N / float(np.mean(dt)) / 1e9, "unit": "GB/s of decoded bytes (host tokens -> host bytes)",
-                          "device_ms": core.last_timings()["device_total_ms"], "ms_per_step": float(np.mean(dt)) * 1e3}
+                          "device_ms": b.core.last_timings()["device_total_ms"], "ms_per_step": float(np.mean(dt)) * 1e3}
     if not args.no_cpu_baseline and world == 1:
-        gbs, mts, desc = cpu_reference_run(pat, ranks, special, text, off, args.cpu_seconds, cores)
+        gbs, mts, desc = cpu_reference_run(b.pat, b.ranks, b.special, b.text, b.off, args.cpu_seconds, cores)
         line["cpu_baseline"] = {"value": gbs, "unit": "GB/s", "mtokens_per_s": mts, **desc}
-    print(json.dumps(line))
+    b.close()
+    del b
+
+    # ---- strong scaling: ONE 1 GiB corpus (the same bytes whatever N), each rank a contiguous 1/N of it
+    if not args.no_extras and args.workload == "config2" and not args.bytes:
+        try:
+            per = ((nbytes // world) // corpus.CHUNK) * corpus.CHUNK
+            lo, hi = rank * per, (nbytes if rank == world - 1 else (rank + 1) * per)
+            part = corpus.generate_range(corpus.ENGLISH, SEEDS["config2"], nbytes, lo, hi)
+            bs = Bench("config2", hi - lo, rank, world, local_rank, text_off=corpus.docs_fixed(part, 65536, at_space=True))
+            ms = measure(bs, args.steps, 2)
+            line["strong"] = {"scaling": "strong", "total_bytes": ms.get("bytes"), "value": ms.get("value"), "unit": "GB/s",
+                              "ms_per_step": ms.get("ms_per_step"), "parity": ms.get("parity"),
+                              "e2e": {k: ms["e2e"][k] for k in ("value", "unit", "ms_per_step")} if ms.get("parity") else None,
+                              "what": f"one {nbytes}-byte corpus (seed {SEEDS['config2']}) split into {world} contiguous shards"}
+            bs.close()
+            del bs
+        except Exception as e:                                       # noqa: BLE001
+            line["strong"] = {"error": repr(e)}
+
+    # ---- the other BASELINE.json configs at their stated sizes (same method: parity gate, value, e2e)
+    if not args.no_configs and args.workload == "config2" and not args.bytes:
+        cfgs = {}
+        for w in ("config3", "config4", "config5", "config1"):
+            try:
+                nb = DEFAULT_BYTES[w]
+                single = w in ("config5", "config1")                 # one document: does not shard -> replicas (DESIGN 5)
+                bw = Bench(w, nb, rank, world, local_rank, seed_offset=0 if single else 7919 * rank)
+                mw = measure(bw, 3, 2)
+                entry = {"config": config_of(w, nb, "replicas (one document cannot shard)" if single else None)}
+                entry["config"]["vocab"] = f"{bw.vocab_src} ({len(bw.ranks)} mergeable ranks)"
+                entry.update({k: mw.get(k) for k in ("parity", "value", "ms_per_step", "mtokens_per_s", "stage_ms", "error")})
+                entry["unit"] = "GB/s"
+                if mw.get("parity"):
+                    entry["e2e"] = {k: mw["e2e"][k] for k in ("value", "unit", "ms_per_step", "identical_to_device_result")}
+                    entry["n_docs_per_gpu"] = bw.n_docs
+                if w == "config1" and rank == 0 and mw.get("parity"):
+                    # plumbing line of BASELINE config 1: token count + sha256 of the uint32 array, GPU vs the reference on CPU
+                    buf = bw.enc.encode_ordinary_packed(bw.text, bw.off)
+                    got = np.array(buf.tokens()); buf.close()
+                    ref, how = load_reference_engine(bw.pat, bw.ranks, bw.special)
+                    t0 = time.perf_counter()
+                    exp = np.asarray(ref.encode_ordinary(bw.text.tobytes().decode()), np.uint32) if ref is not None else None
+                    dt = time.perf_counter() - t0
+                    entry["plumbing"] = {"n_tokens": int(len(got)), "sha256_u32": hashlib.sha256(got.tobytes()).hexdigest(),
+                                         "reference_cpu": how, "reference_sha256_u32": hashlib.sha256(exp.tobytes()).hexdigest() if exp is not None else None,
+                                         "reference_cpu_seconds_1_thread": dt if exp is not None else None,
+                                         "identical": bool(exp is not None and np.array_equal(got, exp))}
+                cfgs[w] = entry
+                bw.close()
+                del bw
+            except Exception as e:                                   # noqa: BLE001
+                cfgs[w] = {"error": repr(e)}
+        line["configs"] = cfgs
+
+    # ---- ONE process driving every GPU of the job through the same C ABI (b200bpe_create_multi): rank 0, the others idle
+    if not args.no_extras and args.workload == "config2" and world > 1 and not args.bytes:
+        barrier()
+        if rank == 0:
+            try:
+                import tiktoken_b200
+                pat, ranks, special, _ = vu.load_encoding("cl100k_base")
+                encm = tiktoken_b200.Encoding("cl100k_multi", pat_str=pat, mergeable_ranks=ranks, special_tokens=special,
+                                              devices=list(range(world)))
+                text, off = corpus.config2(nbytes, SEEDS["config2"])
+                h_text = torch.empty(len(text), dtype=torch.uint8, pin_memory=True); h_text.numpy()[:] = text
+                off64 = off.astype(np.uint64)
+                single = tiktoken_b200.Encoding("cl100k_single", pat_str=pat, mergeable_ranks=ranks, special_tokens=special, device=0)
+                ref_buf = single.encode_ordinary_packed(h_text.numpy(), off64)
+                encm.encode_ordinary_packed(h_text.numpy(), off64).close()
+                ts = []
+                for i in range(3):
+                    t0 = time.perf_counter()
+                    buf = encm.encode_ordinary_packed(h_text.numpy(), off64); ts.append(time.perf_counter() - t0)
+                    if i == 0:
+                        same = bool(np.array_equal(buf.tokens(), ref_buf.tokens()) and np.array_equal(buf.offsets(), ref_buf.offsets()))
+                    buf.close()
+                ref_buf.close()
+                line["one_process_multi_gpu"] = {"devices": world, "value": len(text) / float(np.mean(ts)) / 1e9, "unit": "GB/s",
+                                                 "ms_per_step": float(np.mean(ts)) * 1e3, "identical_to_single_gpu_result": same,
+                                                 "what": "Encoding(devices=[0..N-1]).encode_ordinary_packed on ONE 1 GiB pinned corpus, one process"}
+                del encm, single
+            except Exception as e:                                   # noqa: BLE001
+                line["one_process_multi_gpu"] = {"error": repr(e)}
+        barrier()
+
+    if rank == 0:
+        print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
     return 0

@@ -28,6 +28,10 @@ extern "C" {
 #define B200BPE_ENOBYTE  -5   /* a piece needed a single-byte token the vocabulary lacks
                                  (reference: `ranks[...]` index panic, lib.rs:202,207)         */
 #define B200BPE_EKEY     -6   /* unknown token id in decode (-> KeyError, py.rs:160)           */
+#define B200BPE_ESPECIAL -7   /* the text contains a disallowed special token (-> ValueError,
+                                 tiktoken/core.py:120-124, :431-438)                           */
+#define B200BPE_ECAPACITY -8  /* a device work-space had to grow while several asynchronous device
+                                 calls were queued: re-issue them (b200bpe_device_wait)         */
 
 typedef struct b200bpe b200bpe_t;
 typedef struct b200bpe_result b200bpe_result_t;
@@ -43,6 +47,22 @@ int b200bpe_create(const uint8_t *tok_bytes, const uint64_t *tok_off, const uint
                    uint32_t n_sp,
                    const char *pat_str, int device, b200bpe_t **out);
 
+/* The same constructor for ONE engine spread over several GPUs of the box (`const int* devices,
+ * int n_dev`): the tables are replicated on every listed device; the host-buffer entry points below cut a batch at
+ * document boundaries into chunks that go round-robin over the devices (documents are independent haystacks,
+ * src/lib.rs:360-373) and place every chunk's tokens at its final offset of one pinned result buffer -- the count
+ * "gather" is a host prefix sum, no token payload crosses NVLink.  The device-resident entry points use devices[0]. */
+int b200bpe_create_multi(const uint8_t *tok_bytes, const uint64_t *tok_off, const uint32_t *tok_rank,
+                         uint32_t n_tok,
+                         const uint8_t *sp_bytes, const uint64_t *sp_off, const uint32_t *sp_rank,
+                         uint32_t n_sp,
+                         const char *pat_str, const int *devices, int n_dev, b200bpe_t **out);
+
+/* Number of devices an engine runs on. */
+int b200bpe_n_devices(b200bpe_t *h);
+
+/* Outstanding results keep the engine alive: with results not yet freed this only marks the handle dead and the
+ * last b200bpe_result_free tears it down (TiktokenBuffer owns its Vec in the reference, src/py.rs:186-189). */
 void b200bpe_destroy(b200bpe_t *h);
 
 /* The batched form of CoreBPE::encode_ordinary (src/lib.rs:360-373, py.rs:29-32) as fanned out
@@ -61,6 +81,17 @@ int b200bpe_encode_ordinary_batch(b200bpe_t *h, const uint8_t *text, const uint6
 int b200bpe_encode_batch(b200bpe_t *h, const uint8_t *text, const uint64_t *doc_off, uint64_t n_docs,
                          const uint8_t *allowed, b200bpe_result_t **out);
 
+/* CoreBPE::encode (src/lib.rs:375-442) together with the disallowed-special check that Encoding.encode /
+ * encode_batch run first (tiktoken/core.py:120-124, :197-204, :431-438), both as ONE multi-pattern scan on the device.
+ * flags[i] for special token i (index into the arrays given to b200bpe_create): 1 = allowed (cuts its document into
+ * haystacks, emitted as its own id), 2 = disallowed (its presence anywhere fails the call with B200BPE_ESPECIAL and
+ * *special_index = the leftmost offending special), 0 = ordinary text.  flags == NULL: no special handling. */
+int b200bpe_encode_batch_special(b200bpe_t *h, const uint8_t *text, const uint64_t *doc_off, uint64_t n_docs,
+                                 const uint8_t *flags, b200bpe_result_t **out, int32_t *special_index);
+
+/* Name of special token `index` (as given to b200bpe_create), or NULL. */
+const char *b200bpe_special_name(b200bpe_t *h, int32_t index);
+
 /* Device-resident form of the same path, for measurement and for callers that already hold the
  * corpus in HBM: d_text (n_bytes, readable up to n_bytes+16), d_doc_off (n_docs+1), outputs
  * d_tokens (capacity n_bytes uint32) and d_tok_off (n_docs+1) are DEVICE pointers on the
@@ -69,6 +100,17 @@ int b200bpe_encode_batch(b200bpe_t *h, const uint8_t *text, const uint64_t *doc_
 int b200bpe_encode_device(b200bpe_t *h, const uint8_t *d_text, uint64_t n_bytes,
                           const uint64_t *d_doc_off, uint64_t n_docs,
                           uint32_t *d_tokens, uint64_t *d_tok_off, uint64_t *n_tokens, void *stream);
+
+/* The same, split in two so that a stream of batches never stops for the host: `_async` only enqueues the kernels on
+ * `stream` (no synchronisation; d_counts, if not NULL, is a DEVICE uint64[2] that receives {n_tokens, n_docs} at the
+ * end of the pipeline, e.g. as the send buffer of an NCCL all-gather enqueued behind it); `b200bpe_device_wait`
+ * waits for the most recent call, returns its token count and reports errors.  Work-spaces are sized from
+ * experience, not for the worst case: if one was too small the wait re-runs the LAST call after growing it; with
+ * several calls queued that is reported as B200BPE_ECAPACITY (issue a synchronous call first to settle the sizes). */
+int b200bpe_encode_device_async(b200bpe_t *h, const uint8_t *d_text, uint64_t n_bytes,
+                                const uint64_t *d_doc_off, uint64_t n_docs,
+                                uint32_t *d_tokens, uint64_t *d_tok_off, uint64_t *d_counts, void *stream);
+int b200bpe_device_wait(b200bpe_t *h, uint64_t *n_tokens);
 
 /* CoreBPE::encode_single_piece (src/py.rs:145-150): BPE of raw bytes without the regex split. */
 int b200bpe_encode_single_piece(b200bpe_t *h, const uint8_t *piece, uint64_t len, b200bpe_result_t **out);

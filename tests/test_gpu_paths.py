@@ -224,3 +224,120 @@ def test_reference_host_class_runs_on_the_b200_core(monkeypatch):
     enc2 = pickle.loads(pickle.dumps(enc))                                                 # by value (not in the registry)
     assert isinstance(enc2._core_bpe, shim.CoreBPE)
     assert enc2.encode_ordinary("pickled hello") == o.encode_ordinary("pickled hello")
+
+
+def test_device_special_scan_edge_cases():
+    """The multi-pattern scan behind CoreBPE::encode (lib.rs:375-442) and the disallowed check (core.py:120-124):
+    specials longer than 16 bytes, a thousand reserved specials (o200k_harmony style), specials at document ends,
+    adjacent and self-overlapping occurrences, look-alikes, and the leftmost disallowed special in a batch."""
+    import tiktoken_b200
+    pat, ranks, _, _ = vu.load_encoding("o200k_base", allow_real=False)
+    base = max(ranks.values()) + 1
+    special = {"<|endoftext|>": base, "<|endofprompt|>": base + 1, "<|a|>": base + 2, "aXa": base + 3,
+               "<|start_of_a_very_long_special_token_name|>": base + 4}
+    special.update({f"<|reserved_{i}|>": base + 10 + i for i in range(1000)})
+    e = tiktoken_b200.Encoding("sp_edge", pat_str=pat, mergeable_ranks=ranks, special_tokens=special)
+    o = _oracle(ranks, special, pat)
+    allowed = set(special)
+    docs = ["<|endoftext|>", "<|endoftext|><|endoftext|>", "x<|a|>", "<|a|>x", "a  <|endoftext|>b", "a  b",
+            "<|start_of_a_very_long_special_token_name|> tail", "head <|reserved_7|><|reserved_999|> <|reserved_1000|>",
+            "aXaXa aXaXaXa XaXaX", "<|endoftext", "|endoftext|>", "<|<|a|>|>", "", "日本語<|a|>日本語" * 50,
+            "   <|endofprompt|>\n\n  \n<|a|>   ", "<|a|>" * 300, "no specials here at all " * 100]
+    assert e.encode_batch(docs, allowed_special="all") == [o.encode(d, allowed) for d in docs]
+    for only in ({"<|a|>"}, {"aXa"}, {"<|reserved_7|>", "<|endoftext|>"}):
+        assert e.encode_batch(docs, allowed_special=only, disallowed_special=()) == [o.encode(d, only) for d in docs]
+    for d in docs:                                                   # the single-text entry point of py.rs:34-49
+        assert e.encode(d, allowed_special="all") == o.encode(d, allowed)
+    # default policy: everything not allowed is disallowed -> ValueError naming the LEFTMOST offender of the batch
+    with pytest.raises(ValueError, match="disallowed special token '<\\|a\\|>'"):
+        e.encode_batch(["fine", "x <|a|> then <|endoftext|>", "<|endoftext|>"], allowed_special={"<|endoftext|>"})
+    with pytest.raises(ValueError, match="disallowed special token '<\\|reserved_5\\|>'"):
+        e.encode_batch(["fine", "<|reserved_5|>"])
+    assert e.encode_batch(["fine", "no <| specials |> here"]) == [o.encode_ordinary("fine"), o.encode_ordinary("no <| specials |> here")]
+    # a special split across two documents is not a special
+    assert e.encode_batch(["<|endof", "text|>"], allowed_special="all") == [o.encode_ordinary("<|endof"), o.encode_ordinary("text|>")]
+    # array form: zero-copy pinned result, same tokens
+    text = np.frombuffer("".join(docs).encode(), np.uint8)
+    off = np.zeros(len(docs) + 1, np.uint64)
+    off[1:] = np.cumsum([len(d.encode()) for d in docs])
+    with e.encode_packed(text, off, allowed_special="all") as buf:
+        flat = [t for d in docs for t in o.encode(d, allowed)]
+        assert buf.tokens().tolist() == flat
+
+
+def test_ranks_of_2_pow_24_and_above_take_the_lane_per_piece_kernel():
+    """Token ids beyond 24 bits cannot be packed into the group kernel's keys: those vocabularies run the
+    one-piece-per-lane kernel (and decode through the host maps)."""
+    import tiktoken_b200
+    rnd = random.Random(3)
+    ranks = {bytes([i]): i for i in range(256)}
+    toks = set()
+    while len(toks) < 50:
+        toks.add("".join(rnd.choice("abcd") for _ in range(rnd.choice([2, 2, 3, 4, 6, 9, 20]))).encode())
+    for t, r in zip(sorted(toks), rnd.sample(range(1 << 24, (1 << 24) + 5000), len(toks))):
+        ranks[t] = r
+    e = tiktoken_b200.Encoding("big_ranks", pat_str=vu.CL100K_PAT, mergeable_ranks=ranks, special_tokens={"<|x|>": (1 << 25)})
+    o = _oracle(ranks, {"<|x|>": 1 << 25}, vu.CL100K_PAT)
+    words = ["".join(rnd.choice("abcd") for _ in range(n)) for n in (5, 17, 31, 33, 64, 65, 128, 200, 256, 257, 300) for _ in range(9)]
+    docs = [" ".join(words), words[20], "<|x|>".join(words[:5])]
+    got = e.encode_batch(docs, allowed_special="all")
+    assert got == [o.encode(d, {"<|x|>"}) for d in docs]
+    assert e.decode_batch(got) == docs
+
+
+def test_queued_device_calls_and_count_buffer():
+    import torch
+    import tiktoken_b200
+    pat, ranks, special, _ = vu.load_encoding("cl100k_base", allow_real=False)
+    e = tiktoken_b200.Encoding("async_dev", pat_str=pat, mergeable_ranks=ranks, special_tokens=special)
+    o = _oracle(ranks, special, pat)
+    core = e._core_bpe
+    stream = torch.cuda.Stream()
+    inputs = [corpus.config2(nbytes=(3 + k) << 20, seed=50 + k) for k in range(3)]
+    with torch.cuda.stream(stream):
+        counts = torch.zeros((3, 2), dtype=torch.int64, device="cuda")
+        sets = []
+        for k, (text, off) in enumerate(inputs):
+            d_text = torch.from_numpy(text).cuda(); d_off = torch.from_numpy(off.astype(np.int64)).cuda()
+            d_tok = torch.empty(len(text), dtype=torch.int32, device="cuda"); d_toff = torch.empty(len(off), dtype=torch.int64, device="cuda")
+            sets.append((d_text, d_off, d_tok, d_toff))
+        stream.synchronize()
+        # settle the work-space sizes with one synchronous call on the largest input, then queue three without waiting
+        core.encode_device(sets[2][0].data_ptr(), len(inputs[2][0]), sets[2][1].data_ptr(), len(inputs[2][1]) - 1,
+                           sets[2][2].data_ptr(), sets[2][3].data_ptr(), stream.cuda_stream)
+        for k, (text, off) in enumerate(inputs):
+            d_text, d_off, d_tok, d_toff = sets[k]
+            core.encode_device_async(d_text.data_ptr(), len(text), d_off.data_ptr(), len(off) - 1, d_tok.data_ptr(),
+                                     d_toff.data_ptr(), counts[k].data_ptr(), stream.cuda_stream)
+        n_last = core.device_wait()
+    stream.synchronize()
+    for k, (text, off) in enumerate(inputs):
+        exp_t, exp_o = o.encode_ordinary_batch_np(text, off, CORES)
+        assert counts[k].tolist() == [len(exp_t), len(off) - 1]
+        assert np.array_equal(sets[k][2][:len(exp_t)].cpu().numpy().view(np.uint32), exp_t)
+        assert np.array_equal(sets[k][3].cpu().numpy().astype(np.uint64), exp_o)
+    assert n_last == int(counts[2, 0])
+
+
+
+def test_one_process_multi_gpu_engine():
+    """ONE engine over several GPUs behind the same C ABI -- chunks round-robin over the devices,
+    every chunk's tokens at its final offset of one pinned buffer.  Needs two devices."""
+    import tiktoken_b200
+    from tiktoken_b200 import _lib
+    ndev = int(_lib.lib().b200bpe_device_count())
+    if ndev < 2:
+        pytest.skip("needs at least two CUDA devices")
+    pat, ranks, special, _ = vu.load_encoding("cl100k_base", allow_real=False)
+    e = tiktoken_b200.Encoding("multi", pat_str=pat, mergeable_ranks=ranks, special_tokens=special, devices=list(range(min(ndev, 8))))
+    assert e._core_bpe.devices == list(range(min(ndev, 8)))
+    o = _oracle(ranks, special, pat)
+    text, off = corpus.config2(nbytes=160 << 20, seed=99)
+    exp_t, exp_o = o.encode_ordinary_batch_np(text, off, CORES)
+    for _ in range(2):
+        assert _same(e.encode_ordinary_packed(text, off), exp_t, exp_o)
+    docs = [text[int(off[i]):int(off[i + 1])].tobytes().decode() for i in range(40)] + ["", "<|endoftext|> x"]
+    assert e.encode_batch(docs, allowed_special="all") == [o.encode(d, set(special)) for d in docs]
+    small, soff = corpus.config4(n_docs=50_000, seed=3)
+    exp_t, exp_o = o.encode_ordinary_batch_np(small, soff, CORES)
+    assert _same(e.encode_ordinary_packed(small, soff), exp_t, exp_o)

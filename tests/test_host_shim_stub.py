@@ -35,6 +35,9 @@ class StubLib:
         return 0
 
     # --- engine
+    def b200bpe_create_multi(self, tb, to, tr, n, sb, so, sr, ns, pat, devs, n_dev, out):
+        return self.b200bpe_create(tb, to, tr, n, sb, so, sr, ns, pat, 0, out)
+
     def b200bpe_create(self, tb, to, tr, n, sb, so, sr, ns, pat, dev, out):
         off = self._arr(to, np.uint64, n + 1)
         blob = self._arr(tb, np.uint8, int(off[-1])).tobytes()
@@ -68,13 +71,31 @@ class StubLib:
         return self.b200bpe_encode_batch(h, text, doc_off, n_docs, None, out)
 
     def b200bpe_encode_batch(self, h, text, doc_off, n_docs, allowed, out):
+        return self.b200bpe_encode_batch_special(h, text, doc_off, n_docs, allowed, out, None)
+
+    def b200bpe_encode_batch_special(self, h, text, doc_off, n_docs, flags, out, bad):
+        """flags: 1 = allowed, 2 = disallowed (the device scan's contract, include/b200bpe.h)."""
         o, names, _ = self.engines[h.value]
-        allow = set()
-        if allowed is not None:
-            mask = self._arr(allowed, np.uint8, len(names))
-            allow = {nm for nm, m in zip(names, mask) if m}
+        allow, deny = set(), []
+        if flags is not None:
+            mask = self._arr(flags, np.uint8, len(names))
+            allow = {nm for nm, m in zip(names, mask) if m == 1}
+            deny = [(i, nm) for i, (nm, m) in enumerate(zip(names, mask)) if m == 2]
+        docs = self._docs(text, doc_off, n_docs)
+        if deny:                                              # leftmost occurrence in the packed batch
+            best = None
+            base = 0
+            for d in docs:
+                for i, nm in deny:
+                    k = d.find(nm.encode())
+                    if k >= 0 and (best is None or base + k < best[0]):
+                        best = (base + k, i)
+                base += len(d)
+            if best is not None:
+                bad._obj.value = best[1]
+                return -7
         toks, offs = [], [0]
-        for d in self._docs(text, doc_off, n_docs):
+        for d in docs:
             t = o.encode(d.decode("utf-8"), allow) if allow else o.encode_ordinary(d)
             toks.extend(t)
             offs.append(len(toks))
@@ -225,11 +246,12 @@ def test_pickle_by_value_rebuilds_the_engine(enc):
     assert e2.name == e.name and e2.encode_ordinary("hello world") == o.encode_ordinary("hello world")
 
 
-def test_registry_register_get_and_pickle_by_reference(enc, monkeypatch):
-    """tiktoken/registry.py behaviour: named constructors (here a locally registered one, as a tiktoken_ext plugin
-    would publish it), built once and cached; registered encodings pickle by name (tiktoken/core.py:409-417)."""
+def test_registry_is_the_references_and_pickles_by_reference(enc, monkeypatch):
+    """`tiktoken_b200.get_encoding` serves the constructors the reference's own registry discovers among the
+    `tiktoken_ext` plugins (tiktoken/registry.py) -- here one more entry, as a plugin would publish it -- builds the
+    B200-backed class once per name and pickles it by name (tiktoken/core.py:409-417)."""
+    import tiktoken.registry as ref_registry
     import tiktoken_b200
-    from tiktoken_b200 import registry
     pat, ranks, special, _ = vu.load_encoding("r50k_base", allow_real=False)
     calls = []
 
@@ -237,14 +259,28 @@ def test_registry_register_get_and_pickle_by_reference(enc, monkeypatch):
         calls.append(1)
         return {"name": "r50k_like_local", "pat_str": pat, "mergeable_ranks": ranks, "special_tokens": special}
 
-    monkeypatch.setattr(registry, "ENCODINGS", {})
-    registry.register_encoding("r50k_like_local", ctor)
-    assert "r50k_like_local" in tiktoken_b200.list_encoding_names()
+    tiktoken_b200.list_encoding_names()                          # plugin discovery by the reference's code
+    monkeypatch.setitem(ref_registry.ENCODING_CONSTRUCTORS, "r50k_like_local", ctor)
+    monkeypatch.setattr(tiktoken_b200, "_REGISTRY", {})
+    assert "r50k_like_local" in tiktoken_b200.list_encoding_names() and "cl100k_base" in tiktoken_b200.list_encoding_names()
     e = tiktoken_b200.get_encoding("r50k_like_local")
-    assert tiktoken_b200.get_encoding("r50k_like_local") is e and len(calls) == 1
+    assert isinstance(e, tiktoken_b200.Encoding) and tiktoken_b200.get_encoding("r50k_like_local") is e and len(calls) == 1
     assert pickle.dumps(e) == pickle.dumps(e) and len(pickle.dumps(e)) < 400          # by reference, not 50 k tokens
     assert pickle.loads(pickle.dumps(e)).encode_ordinary("hello") == e.encode_ordinary("hello")
     with pytest.raises(ValueError, match="Unknown encoding"):
         tiktoken_b200.get_encoding("no_such_encoding")
     with pytest.raises(ValueError):
         tiktoken_b200.get_encoding(5)
+
+
+def test_install_swaps_the_native_module_under_the_reference_package(enc, monkeypatch):
+    import tiktoken
+    import tiktoken.core
+    import tiktoken_b200
+    from tiktoken_b200 import _tiktoken as shim
+    monkeypatch.setattr(tiktoken.core, "_tiktoken", tiktoken.core._tiktoken)     # restored after the test
+    tiktoken_b200.install()
+    pat, ranks, special, _ = vu.load_encoding("cl100k_base", allow_real=False)
+    e = tiktoken.Encoding("ref_on_b200", pat_str=pat, mergeable_ranks=ranks, special_tokens=special)
+    assert isinstance(e._core_bpe, shim.CoreBPE)
+    assert e.encode("hello <|endoftext|>", allowed_special="all") == enc[1].encode("hello <|endoftext|>", set(special))

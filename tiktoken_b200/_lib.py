@@ -14,10 +14,11 @@ import subprocess
 
 _CSRC = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc")
 _SO = os.path.join(_CSRC, "libb200bpe.so")
-_SOURCES = ["b200bpe.cu", "bpe_device.cuh", "bpe_tables.h", "pretok_rules.cuh", "pretok_fast.cuh", "text_access.cuh",
-            "unicode_classes.inc"]
+_SOURCES = ["b200bpe.cu", "dev_common.cuh", "kernels_pretok.cuh", "kernels_long.cuh", "kernels_mid.cuh", "kernels_encode.cuh",
+            "kernels_special.cuh", "kernels_decode.cuh", "bpe_device.cuh", "bpe_tables.h", "pretok_rules.cuh",
+            "pretok_fast.cuh", "text_access.cuh", "unicode_classes.inc"]
 
-OK, EINVAL, EPATTERN, EDUPRANK, ECUDA, ENOBYTE, EKEY = 0, -1, -2, -3, -4, -5, -6
+OK, EINVAL, EPATTERN, EDUPRANK, ECUDA, ENOBYTE, EKEY, ESPECIAL, ECAPACITY = 0, -1, -2, -3, -4, -5, -6, -7, -8
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-shared", "-Xcompiler", "-fPIC"]
@@ -44,14 +45,27 @@ def lib() -> C.CDLL:
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(_SO):
+    so = os.environ.get("B200BPE_LIB") or _SO        # development: A/B builds of the same sources (tools/ab.sh)
+    if not os.path.exists(so):
         raise RuntimeError(
-            f"{_SO} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            f"{so} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
             "(tiktoken_b200 has no CPU fallback)")
-    L = C.CDLL(_SO)
+    L = C.CDLL(so)
     vp, u64, u32, i32 = C.c_void_p, C.c_uint64, C.c_uint32, C.c_int
     L.b200bpe_create.restype = i32
     L.b200bpe_create.argtypes = [vp, vp, vp, u32, vp, vp, vp, u32, C.c_char_p, i32, C.POINTER(vp)]
+    L.b200bpe_create_multi.restype = i32
+    L.b200bpe_create_multi.argtypes = [vp, vp, vp, u32, vp, vp, vp, u32, C.c_char_p, vp, i32, C.POINTER(vp)]
+    L.b200bpe_n_devices.restype = i32
+    L.b200bpe_n_devices.argtypes = [vp]
+    L.b200bpe_encode_batch_special.restype = i32
+    L.b200bpe_encode_batch_special.argtypes = [vp, vp, vp, u64, vp, C.POINTER(vp), C.POINTER(C.c_int32)]
+    L.b200bpe_special_name.restype = C.c_char_p
+    L.b200bpe_special_name.argtypes = [vp, C.c_int32]
+    L.b200bpe_encode_device_async.restype = i32
+    L.b200bpe_encode_device_async.argtypes = [vp, vp, u64, vp, u64, vp, vp, vp, vp]
+    L.b200bpe_device_wait.restype = i32
+    L.b200bpe_device_wait.argtypes = [vp, C.POINTER(u64)]
     L.b200bpe_destroy.restype = None
     L.b200bpe_destroy.argtypes = [vp]
     L.b200bpe_encode_ordinary_batch.restype = i32
@@ -93,7 +107,8 @@ EXPORTS = [
     "b200bpe_encode_device", "b200bpe_encode_single_piece", "b200bpe_result_tokens",
     "b200bpe_result_offsets", "b200bpe_result_n_tokens", "b200bpe_result_n_docs", "b200bpe_result_free",
     "b200bpe_decode_bytes", "b200bpe_decode_batch", "b200bpe_last_timings", "b200bpe_table_bytes", "b200bpe_last_error",
-    "b200bpe_version", "b200bpe_device_count",
+    "b200bpe_version", "b200bpe_device_count", "b200bpe_create_multi", "b200bpe_n_devices", "b200bpe_encode_batch_special",
+    "b200bpe_special_name", "b200bpe_encode_device_async", "b200bpe_device_wait",
 ]
 
 
@@ -106,7 +121,7 @@ def check(rc: int) -> None:
     if rc == OK:
         return
     msg = last_error()
-    if rc in (EINVAL, EPATTERN, EDUPRANK):
+    if rc in (EINVAL, EPATTERN, EDUPRANK, ESPECIAL):
         raise ValueError(msg)
     if rc == EKEY:
         raise KeyError(msg)

@@ -83,18 +83,30 @@ class TokenBuffer:
         self.close()
 
 
+class DisallowedSpecial(ValueError):
+    """The text contains a special token that the call disallows; `.token` names it.  The host class turns it into
+    the reference's message (tiktoken/core.py:431-438)."""
+
+    def __init__(self, token: str):
+        super().__init__(f"Encountered text corresponding to disallowed special token {token!r}.")
+        self.token = token
+
+
 class CoreBPE:
     def __init__(self, mergeable_ranks: dict[bytes, int], special_tokens: dict[str, int], pat_str: str,
-                 device: int | None = None):
+                 device: int | None = None, devices: list[int] | None = None):
+        """Same positional arguments as the reference's `CoreBPE(encoder, special_tokens_encoder, pattern)`
+        (src/py.rs:16-23).  `device` / `devices` (keyword, optional) choose the GPU(s): one engine can span several
+        GPUs of the box (b200bpe_create_multi), documents then shard over them inside every batch call."""
         toks = list(mergeable_ranks.keys())
         blob, off = _flatten_bytes(toks)
         ranks = np.fromiter((mergeable_ranks[t] for t in toks), dtype=np.uint32, count=len(toks))
-        self._create(blob, off, ranks, special_tokens, pat_str, device)
+        self._create(blob, off, ranks, special_tokens, pat_str, device, devices)
         self._encoder_dict = mergeable_ranks
 
     @classmethod
     def from_flat(cls, tok_bytes: np.ndarray, tok_off: np.ndarray, tok_rank: np.ndarray, special_tokens: dict[str, int],
-                  pat_str: str, device: int | None = None) -> "CoreBPE":
+                  pat_str: str, device: int | None = None, devices: list[int] | None = None) -> "CoreBPE":
         """Construct from the flattened vocabulary (token i = tok_bytes[tok_off[i]:tok_off[i+1]], rank
         tok_rank[i]) -- what `_b200pack.parse_tiktoken` produces from a `.tiktoken` file -- without a Python
         dict of 100-200 k bytes objects ("next" row: vocabulary parsing, tiktoken/load.py:159-171).  The dict the
@@ -105,13 +117,13 @@ class CoreBPE:
         ranks = np.ascontiguousarray(tok_rank, np.uint32)
         if len(off) != len(ranks) + 1 or (len(off) and int(off[-1]) > len(blob)):
             raise ValueError("inconsistent flattened vocabulary")
-        self._create(blob if len(blob) else np.zeros(1, np.uint8), off, ranks, special_tokens, pat_str, device)
+        self._create(blob if len(blob) else np.zeros(1, np.uint8), off, ranks, special_tokens, pat_str, device, devices)
         self._encoder_dict = None
         self._flat = (blob, off, ranks)
         return self
 
     def _create(self, blob: np.ndarray, off: np.ndarray, ranks: np.ndarray, special_tokens: dict[str, int], pat_str: str,
-                device: int | None):
+                device: int | None, devices: list[int] | None = None):
         L = _lib.lib()
         self._L = L
         n_tok = len(ranks)
@@ -120,16 +132,20 @@ class CoreBPE:
         sranks = np.asarray([special_tokens[s] for s in self._special_names], dtype=np.uint32)
         if len(sranks) == 0:
             sranks = np.zeros(1, np.uint32)
-        if device is None:
-            import os
-            device = int(os.environ.get("B200BPE_DEVICE", os.environ.get("LOCAL_RANK", "0")))
+        if devices is None:
+            if device is None:
+                import os
+                device = int(os.environ.get("B200BPE_DEVICE", os.environ.get("LOCAL_RANK", "0")))
+            devices = [int(device)]
+        devs = np.asarray(list(devices), dtype=np.int32)
         h = C.c_void_p()
-        rc = L.b200bpe_create(_ptr(blob), _ptr(off), _ptr(ranks if n_tok else np.zeros(1, np.uint32)),
-                              n_tok, _ptr(sblob), _ptr(soff), _ptr(sranks), len(self._special_names),
-                              pat_str.encode("utf-8"), device, C.byref(h))
+        rc = L.b200bpe_create_multi(_ptr(blob), _ptr(off), _ptr(ranks if n_tok else np.zeros(1, np.uint32)),
+                                    n_tok, _ptr(sblob), _ptr(soff), _ptr(sranks), len(self._special_names),
+                                    pat_str.encode("utf-8"), _ptr(devs), len(devs), C.byref(h))
         _lib.check(rc)                      # ValueError for an unsupported pat_str / duplicate ranks
         self._h = h
-        self.device = device
+        self.device = int(devs[0])
+        self.devices = [int(d) for d in devs]
         self._special = special_tokens
         self._decoder = None
         self._flat = None
@@ -158,11 +174,22 @@ class CoreBPE:
         _lib.check(rc)
         return TokenBuffer(self._L, res, self)
 
-    def encode_batch_buffer(self, text: np.ndarray, doc_off: np.ndarray, allowed_special) -> TokenBuffer:
-        allowed = np.asarray([1 if s in allowed_special else 0 for s in self._special_names] + [0], np.uint8)
+    def encode_batch_buffer(self, text: np.ndarray, doc_off: np.ndarray, allowed_special, disallowed_special=()) -> TokenBuffer:
+        """CoreBPE::encode for a batch (lib.rs:375-442) plus, when `disallowed_special` is given, the check that
+        `Encoding.encode` runs first (core.py:120-124) -- one device scan for both.  Raises the reference's
+        ValueError (through `disallowed_error`) naming the leftmost disallowed special."""
+        flags = np.zeros(len(self._special_names) + 1, np.uint8)
+        for i, s in enumerate(self._special_names):
+            if s in allowed_special:
+                flags[i] = 1
+            elif s in disallowed_special:
+                flags[i] = 2
         res = C.c_void_p()
-        rc = self._L.b200bpe_encode_batch(self._h, _ptr(text), _ptr(doc_off), len(doc_off) - 1, _ptr(allowed),
-                                          C.byref(res))
+        bad = C.c_int32(-1)
+        rc = self._L.b200bpe_encode_batch_special(self._h, _ptr(text), _ptr(doc_off), len(doc_off) - 1, _ptr(flags),
+                                                  C.byref(res), C.byref(bad))
+        if rc == _lib.ESPECIAL:
+            raise DisallowedSpecial(self._special_names[bad.value])
         _lib.check(rc)
         return TokenBuffer(self._L, res, self)
 
@@ -323,6 +350,18 @@ class CoreBPE:
         b = (C.c_uint64 * 4)()
         self._L.b200bpe_table_bytes(self._h, b)
         return {"piece_table": int(b[0]), "pair_table": int(b[1]), "long_token_table": int(b[2]), "unicode": int(b[3])}
+
+    def encode_device_async(self, d_text_ptr: int, n_bytes: int, d_doc_off_ptr: int, n_docs: int, d_tokens_ptr: int,
+                            d_tok_off_ptr: int, d_counts_ptr: int = 0, stream: int = 0) -> None:
+        """Enqueue only (no host synchronisation); `d_counts_ptr`: optional device uint64[2] <- {n_tokens, n_docs}."""
+        _lib.check(self._L.b200bpe_encode_device_async(self._h, C.c_void_p(d_text_ptr), n_bytes, C.c_void_p(d_doc_off_ptr),
+                                                       n_docs, C.c_void_p(d_tokens_ptr), C.c_void_p(d_tok_off_ptr),
+                                                       C.c_void_p(d_counts_ptr), C.c_void_p(stream)))
+
+    def device_wait(self) -> int:
+        n = C.c_uint64(0)
+        _lib.check(self._L.b200bpe_device_wait(self._h, C.byref(n)))
+        return int(n.value)
 
     def encode_device(self, d_text_ptr: int, n_bytes: int, d_doc_off_ptr: int, n_docs: int, d_tokens_ptr: int,
                       d_tok_off_ptr: int, stream: int = 0) -> int:

@@ -232,9 +232,32 @@ B2_HD uint32_t merge_short(const DevTables &T, ByteFn byte_at, int n, IdArr id, 
 #define B2_ANY(group, pred) (pred)
 #endif
 
-template <class ByteFn, class IdArr, class RkArr>
+template <int MAXN = 16, class ByteFn, class IdArr, class RkArr>
 B2_HD uint32_t merge_short_conv(const DevTables &T, ByteFn byte_at, int n, int n_max, unsigned group,
                                 IdArr id, RkArr rk) {
+#if defined(__CUDA_ARCH__)
+    // initial ids / pair ranks, 16 parts at a time: all table loads of a block are issued before the first store
+    // waits for one (a rolled loop serialises one L2 round trip per part)
+#pragma unroll
+    for (int h = 0; h < MAXN; h += 16) {
+        if (h < n_max) {
+            uint32_t iv[16], rv[16];
+#pragma unroll
+            for (int k = 0; k < 16; k++) {
+                const int j = h + k;
+                iv[k] = 0; rv[k] = RANK_MAX;
+                if (j < n) {
+                    const uint32_t b0 = byte_at(j);
+                    iv[k] = B2_LDG_U32(T.byte_id + b0);
+                    if (j + 1 < n) rv[k] = B2_LDG_U32(T.pair2 + (b0 << 8 | byte_at(j + 1)));
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < 16; k++)
+                if (h + k < n_max) { id[h + k] = iv[k]; rk[h + k] = rv[k]; }
+        }
+    }
+#else
     for (int j = 0; j < n_max; j++) {
         uint32_t i0 = 0, r0 = RANK_MAX;
         if (j < n) {
@@ -244,6 +267,7 @@ B2_HD uint32_t merge_short_conv(const DevTables &T, ByteFn byte_at, int n, int n
         }
         id[j] = i0; rk[j] = r0;
     }
+#endif
     uint32_t mask = n <= 0 ? 0u : ((n >= 32) ? 0xFFFFFFFFu : ((1u << n) - 1u));
     for (;;) {
         uint32_t best = RANK_MAX; int bj = 0;

@@ -18,7 +18,7 @@ struct HostTables {
     std::vector<U4> piece_tab; uint32_t piece_mask = 0;
     std::vector<U4> long_tab;  uint32_t long_mask = 0;
     std::vector<uint8_t> long_blob;
-    uint32_t max_token_len = 0, n_long_tokens = 0;
+    uint32_t max_token_len = 0, n_long_tokens = 0, max_rank = 0;
     uint64_t n_pairs = 0;
     // decode side (host): rank -> bytes
     std::unordered_map<uint32_t, std::string> decoder;
@@ -73,6 +73,7 @@ inline int build_tables(const uint8_t *tok_bytes, const uint64_t *tok_off, const
             return -3;
         }
         if (len > H.max_token_len) H.max_token_len = (uint32_t)len;
+        if (tok_rank[i] > H.max_rank) H.max_rank = tok_rank[i];
     }
     H.byte_id.assign(256, 0);
     for (int b = 0; b < 256; b++) {

@@ -16,26 +16,6 @@ namespace b2bpe {
 
 struct SpanStats { unsigned long long positions, slow; };
 
-// Next-round rules, verified on the CPU (tests/test_pretok_rules.py builds the host check with it) but not yet
-// measured / validated on the GPU: the shipped kernels are compiled with it OFF.
-#ifndef B2_O200K_FAST_PREFIX
-#define B2_O200K_FAST_PREFIX 0
-#endif
-#ifndef B2_O200K_FAST_APOS
-#define B2_O200K_FAST_APOS 0
-#endif
-#ifndef B2_R50K_FAST_CONTRACTION
-#define B2_R50K_FAST_CONTRACTION 0
-#endif
-#ifndef B2_O200K_FAST_WSNL
-#define B2_O200K_FAST_WSNL 0
-#endif
-#ifndef B2_CL100K_FAST_WSNL
-#define B2_CL100K_FAST_WSNL 0
-#endif
-#ifndef B2_CL100K_FAST_CONTRACTION
-#define B2_CL100K_FAST_CONTRACTION 0
-#endif
 
 #if defined(__CUDA_ARCH__)
 #define B2_CTZLL(x) (__ffsll((long long)(x)) - 1)
@@ -170,37 +150,7 @@ B2_HD uint64_t span_fast(const TextAccess &t, int64_t w, uint64_t &slow_out, Spa
         b |= WSany & (~pWSany | nextNonWs);
         slow |= WSany & m.hi & pWSany;
         b |= L & ~(pL | pSP);
-#if B2_R50K_FAST_CONTRACTION
-        // Letters up to three bytes behind an apostrophe a, decided per apostrophe.  `'(?:[sdmt]|ll|ve|re)` is the first
-        // alternative and case-sensitive ASCII: when a piece starts at a and the suffix matches, the suffix letters
-        // continue that piece and the next letter starts one; otherwise the apostrophe is punctuation and the letter
-        // after it starts a word (the default of the rule above).
-        {
-            const uint64_t starts = m.APOS & (~(pX | pSP) | m.D);
-            uint64_t und_after = L & pAPOS & own, und_near = L & pL & aposNear & own;
-            for (uint64_t aps = m.APOS & ((und_after >> 1) | (und_near >> 2) | (und_near >> 3)); aps;) {
-                const int j = B2_CTZLL(aps); aps &= aps - 1;
-                const uint64_t a1 = 1ull << (j + 1), a2 = a1 << 1, a3 = a2 << 1;
-                bool c1ok = false, c2ok = false;                       // 1-letter / 2-letter contraction at this apostrophe
-                if ((L & a1) && !(m.hi & a1) && !(m.D & a1) && ((starts >> j) & 1ull)) {
-                    const unsigned c1 = t.text[win0 + j + 1];
-                    c1ok = c1 == 's' || c1 == 'd' || c1 == 'm' || c1 == 't';
-                    if (!c1ok && (L & a2) && !(m.hi & a2) && !(m.D & a2)) {
-                        const unsigned c2 = t.text[win0 + j + 2];
-                        c2ok = (c1 == 'l' && c2 == 'l') || (c1 == 'v' && c2 == 'e') || (c1 == 'r' && c2 == 'e');
-                    }
-                }
-                if (und_after & a1) { if (c1ok || c2ok) b &= ~a1; und_after &= ~a1; }
-                if (und_near & a2) { if (c1ok) b |= a2; und_near &= ~a2; }
-                // a+3 is this apostrophe's business only behind two letters; behind another apostrophe at a+1 (it may start
-                // a document) it is that one's
-                if ((und_near & a3) && !(m.APOS & a1)) { if (c2ok) b |= a3; und_near &= ~a3; }
-            }
-            slow |= und_after | und_near;
-        }
-#else
         slow |= L & (pAPOS | (pL & aposNear));
-#endif
         b |= m.N & ~(pN | pSP);
         b |= X & ~(pX | pSP);
     } else if (PAT == PAT_CL100K) {
@@ -209,7 +159,6 @@ B2_HD uint64_t span_fast(const TextAccess &t, int64_t w, uint64_t &slow_out, Spa
         // letters
         b |= L & (pN | pNL);
         b |= L & pX & ~pHi & ~(m.D << 1) & ((X | m.SP) << 2);
-#if B2_CL100K_FAST_CONTRACTION
         // Letters next to an apostrophe a (the only undecided positions of English text).  The letter at a+1 needs
         // nothing special: whether a starts `'s` or is the one-scalar prefix of a word, no piece starts at a+1
         // when one starts at a, and the rule above covers an apostrophe inside a punctuation run.  The letters at
@@ -242,9 +191,6 @@ B2_HD uint64_t span_fast(const TextAccess &t, int64_t w, uint64_t &slow_out, Spa
             }
             slow |= und;
         }
-#else
-        slow |= L & ((pX & pHi) | pAPOS | (pL & aposNear));
-#endif
         // digits: groups of three from the run start
         b |= m.N & ~pN;
         {   // `\p{N}{1,3}`: a digit starts a piece iff the count of digits before it in its run is a
@@ -268,64 +214,11 @@ B2_HD uint64_t span_fast(const TextAccess &t, int64_t w, uint64_t &slow_out, Spa
         b |= m.NL & (pL | pN);
         b |= WSnn & ~pWSany;
         b |= WSnn & pWSnn & nextNonWs;
-#if B2_CL100K_FAST_WSNL
-        // Whitespace right after CR/LF (the first indentation character of every line of code).  `\s++$` / `\s*[\r\n]`
-        // swallow it iff its whitespace run reaches the document end or another CR/LF; then it still starts a piece
-        // when the CR/LFs before it were the `[\r\n]*+` tail of a punctuation piece.  Both are reachability questions
-        // along runs: solved for all positions at once by propagating seeds through run links with doubling shifts;
-        // runs that leave the window stay with the general function.
-        slow |= WSnn & m.hi & pWSany;
-        {
-            const uint64_t cand = WSnn & pNL & own;
-            if (cand) {
-                const uint64_t nd1 = ~(m.D >> 1);                                   // no document starts at i+1
-                const int64_t last = t.n - 1 - win0;                                // the window's last byte is NOT an end
-                const uint64_t text_end = (last >= 0 && last < 48) ? (1ull << last) : 0ull;
-                const uint64_t end_after = m.valid & ((m.D >> 1) | text_end);       // i is the last byte of its document
-                const uint64_t known_cls = m.valid & ~unk0;
-                // forward: SW = whitespace from which only whitespace leads to a CR/LF or to the document end;
-                //          KN = whitespace whose run ends (in anything known) inside the window
-                uint64_t sw = WSnn & (((m.NL >> 1) & nd1) | end_after);
-                uint64_t kn = WSnn & ((((known_cls & ~WSnn) >> 1) & nd1) | end_after);
-                uint64_t link = WSnn & (WSnn >> 1) & nd1;                           // i and i+1: whitespace of one document
-                sw |= link & (sw >> 1); kn |= link & (kn >> 1);
-                uint64_t l2 = link & (link >> 1);
-                sw |= l2 & (sw >> 2); kn |= l2 & (kn >> 2);
-                uint64_t l4 = l2 & (l2 >> 2);
-                sw |= l4 & (sw >> 4); kn |= l4 & (kn >> 4);
-                uint64_t l8 = l4 & (l4 >> 4);
-                sw |= l8 & (sw >> 8); kn |= l8 & (kn >> 8);
-                uint64_t l16 = l8 & (l8 >> 8);
-                sw |= l16 & (sw >> 16); kn |= l16 & (kn >> 16);
-                uint64_t l32 = l16 & (l16 >> 16);
-                sw |= l32 & (sw >> 32); kn |= l32 & (kn >> 32);
-                // backward: TL = CR/LF reached from a punctuation scalar through CR/LFs only;  KB = CR/LF whose run
-                //           starts (after anything known, or at a document start) inside the window
-                const uint64_t oth = m.O | m.M | m.APOS | m.SLASH;
-                const uint64_t nd0 = ~m.D;                                         // i does not start a document
-                uint64_t tl = m.NL & (oth << 1) & nd0;
-                uint64_t kb = m.NL & ((((known_cls & ~m.NL) << 1)) | m.D);
-                uint64_t bl = m.NL & (m.NL << 1) & nd0;                            // i-1 and i: CR/LF of one document
-                tl |= bl & (tl << 1); kb |= bl & (kb << 1);
-                uint64_t b2 = bl & (bl << 1);
-                tl |= b2 & (tl << 2); kb |= b2 & (kb << 2);
-                uint64_t b4 = b2 & (b2 << 2);
-                tl |= b4 & (tl << 4); kb |= b4 & (kb << 4);
-                const uint64_t fwd_known = kn, swl = sw;
-                // decided: run end known, and either not swallowed or the CR/LF run before it is known too
-                const uint64_t dec = cand & fwd_known & (~swl | (kb << 1));
-                b |= dec & (~swl | (tl << 1));
-                slow |= cand & ~dec;
-            }
-        }
-#else
         slow |= WSnn & (pNL | (m.hi & pWSany));
-#endif
     } else {
         const uint64_t Xo = m.O | m.APOS | m.SLASH;
-        const uint64_t pXo = Xo << 1, pM = m.M << 1, pLB = m.LB << 1, pLL = m.LL << 1, pLU = m.LU << 1;
+        const uint64_t pM = m.M << 1, pLB = m.LB << 1, pLL = m.LL << 1, pLU = m.LU << 1;
         const uint64_t low = m.LL | m.LB;                           // extends any word
-#if B2_O200K_FAST_PREFIX
         b |= low & (pN | pNL);
         b |= m.LU & (pLL | pN | pNL);
         // A letter right after an "other" scalar x (punctuation, symbol; not apostrophe / slash / mark): x is either
@@ -344,7 +237,6 @@ B2_HD uint64_t span_fast(const TextAccess &t, int64_t w, uint64_t &slow_out, Spa
             const uint64_t letter_after_o = (low | m.LU) & pO;
             b |= letter_after_o & x0;
             slow |= letter_after_o & ~(x0 | x1);
-#if B2_O200K_FAST_APOS
             // Apostrophes, and the letters up to three bytes behind one, decided per apostrophe (they are sparse):
             //  * after a word character, `'s|'t|'re|'ve|'m|'ll|'d` (ASCII, any case) is the optional tail of that word's
             //    piece: no piece starts at the apostrophe or inside the suffix, one starts right after it; anything else
@@ -395,23 +287,8 @@ B2_HD uint64_t span_fast(const TextAccess &t, int64_t w, uint64_t &slow_out, Spa
                 if (und_near & a3) { if (set3) b = b3 ? (b | a3) : (b & ~a3); und_near &= ~a3; }
             }
             slow |= und_apos | und_after | und_near;
-#else
-            const uint64_t pXrest = (m.APOS | m.SLASH) << 1;
-            slow |= low & (pXrest | pM | (pL & aposNear));
-            slow |= m.LU & (pLB | pM | pXrest | ((pLL | pLU) & aposNear));
-#endif
         }
-#else
-        b |= low & (pN | pNL);
-        slow |= low & (pXo | pM | (pL & aposNear));
-        b |= m.LU & (pLL | pN | pNL);
-        slow |= m.LU & (pLB | pM | pXo | ((pLL | pLU) & aposNear));
-#endif
-#if B2_O200K_FAST_PREFIX && B2_O200K_FAST_APOS
         slow |= m.M | m.SLASH;
-#else
-        slow |= m.M | m.APOS | m.SLASH;
-#endif
         b |= m.O & (pL | pN | ((m.WS | m.NL) << 1));
         slow |= m.O & (pM | (m.SLASH << 1));
         b |= m.N & ~pN;
@@ -436,51 +313,7 @@ B2_HD uint64_t span_fast(const TextAccess &t, int64_t w, uint64_t &slow_out, Spa
         slow |= m.NL & pM;
         b |= WSnn & ~pWSany;
         b |= WSnn & pWSnn & nextNonWs;
-#if B2_O200K_FAST_WSNL
-        // Whitespace right after CR/LF, as in the cl100k rule above, with o200k's alternatives: `\s*[\r\n]+` swallows
-        // it iff another CR/LF follows in its whitespace run (the document end does not); it still starts a piece when
-        // the CR/LFs before it are the `[\r\n/]*` tail of a punctuation piece, i.e. directly follow an "other" scalar,
-        // apostrophe or slash.  A mark before the CR/LFs may belong to a word: left to the general function.
-        slow |= WSnn & m.hi & pWSany;
-        {
-            const uint64_t cand = WSnn & pNL & own;
-            if (cand) {
-                const uint64_t nd1 = ~(m.D >> 1);
-                const int64_t last = t.n - 1 - win0;
-                const uint64_t text_end = (last >= 0 && last < 48) ? (1ull << last) : 0ull;
-                const uint64_t end_after = m.valid & ((m.D >> 1) | text_end);
-                const uint64_t known_cls = m.valid & ~unk0;
-                uint64_t sw = WSnn & (m.NL >> 1) & nd1;
-                uint64_t kn = WSnn & ((((known_cls & ~WSnn) >> 1) & nd1) | end_after);
-                uint64_t link = WSnn & (WSnn >> 1) & nd1;
-                sw |= link & (sw >> 1); kn |= link & (kn >> 1);
-                uint64_t l2 = link & (link >> 1);
-                sw |= l2 & (sw >> 2); kn |= l2 & (kn >> 2);
-                uint64_t l4 = l2 & (l2 >> 2);
-                sw |= l4 & (sw >> 4); kn |= l4 & (kn >> 4);
-                uint64_t l8 = l4 & (l4 >> 4);
-                sw |= l8 & (sw >> 8); kn |= l8 & (kn >> 8);
-                uint64_t l16 = l8 & (l8 >> 8);
-                sw |= l16 & (sw >> 16); kn |= l16 & (kn >> 16);
-                uint64_t l32 = l16 & (l16 >> 16);
-                sw |= l32 & (sw >> 32); kn |= l32 & (kn >> 32);
-                const uint64_t nd0 = ~m.D;
-                uint64_t tl = m.NL & (Xo << 1) & nd0;
-                uint64_t kb = m.NL & (((known_cls & ~m.NL & ~m.M) << 1) | m.D);
-                uint64_t bl = m.NL & (m.NL << 1) & nd0;
-                tl |= bl & (tl << 1); kb |= bl & (kb << 1);
-                uint64_t b2 = bl & (bl << 1);
-                tl |= b2 & (tl << 2); kb |= b2 & (kb << 2);
-                uint64_t b4 = b2 & (b2 << 2);
-                tl |= b4 & (tl << 4); kb |= b4 & (kb << 4);
-                const uint64_t dec = cand & kn & (~sw | (kb << 1));
-                b |= dec & (~sw | (tl << 1));
-                slow |= cand & ~dec;
-            }
-        }
-#else
         slow |= WSnn & (pNL | (m.hi & pWSany));
-#endif
     }
     // anything that touches an undecoded (truncated / unknown) non-ASCII byte goes the slow way
     const uint64_t unk = unk0;

@@ -60,52 +60,69 @@ def encode_sharded(encode_packed, text: np.ndarray, doc_off: np.ndarray, rank: i
 
 
 class CountExchange:
-    """The same all-gather as `gather_counts`, posted asynchronously on preallocated buffers so that a
-    stream of batches does not stop for it: `post()` after batch k, `wait()` (any time later) returns
-    (counts[world,2], token_base, doc_base) of that batch.  With an NCCL group the exchange runs on the
-    communicator's stream next to the kernels of batch k+1; the placement is only needed when the shard
-    is written out."""
+    """The same all-gather as `gather_counts`, posted asynchronously so that a stream of batches does not stop
+    for it: `post()` after batch k, `wait()` (any time later) returns (counts[world,2], token_base, doc_base) of
+    that batch.  All buffers are allocated ONCE (a ring of `depth` send / receive pairs): a post costs one
+    `all_gather_into_tensor` and nothing else.  The send buffer of slot k can be handed to the engine as the
+    `d_counts` of `b200bpe_encode_device_async` (`send_ptr(k)`): the pipeline's last kernel writes {n_tokens, n_docs}
+    there and `post_device()` enqueues the all-gather behind it on the same stream -- the host never sees the
+    counts.  With an NCCL group the exchange runs next to the kernels of the following batch."""
 
-    def __init__(self, rank: int, world: int, device=None):
+    def __init__(self, rank: int, world: int, device=None, depth: int = 8):
+        self.rank, self.world, self.depth = rank, world, depth
+        self._pending = []
+        self._k = 0
         import torch
         import torch.distributed as dist
-        self.rank, self.world = rank, world
         self.active = world > 1 and dist.is_initialized()
-        self._pending = []
-        if self.active:
-            self._dev = device or "cpu"
-            self._pool = []                                  # reusable (host, mine, gathered) buffer sets
-
-    def _buffers(self):
-        import torch
-        if self._pool:
-            return self._pool.pop()
+        self._dev = device or "cpu"
+        self._send = torch.zeros((depth, 2), dtype=torch.int64, device=self._dev)
+        self._recv = torch.zeros((depth, max(world, 1), 2), dtype=torch.int64, device=self._dev)
         pin = self._dev != "cpu" and torch.cuda.is_available()
-        host = torch.zeros(2, dtype=torch.int64, pin_memory=pin)
-        mine = torch.zeros(2, dtype=torch.int64, device=self._dev)
-        gathered = [torch.zeros(2, dtype=torch.int64, device=self._dev) for _ in range(self.world)]
-        return host, mine, gathered
+        self._host = torch.zeros((depth, 2), dtype=torch.int64, pin_memory=pin)
+
+    def _slot(self) -> int:
+        if len(self._pending) >= self.depth:
+            raise RuntimeError("CountExchange ring is full: wait() before posting more")
+        k = self._k
+        self._k = (k + 1) % self.depth
+        return k
+
+    def send_ptr(self, k: int | None = None) -> int:
+        """Device address of the next (or given) slot's send buffer, for `encode_device_async(d_counts_ptr=...)`."""
+        return int(self._send[self._k if k is None else k].data_ptr())
 
     def post(self, n_tokens: int, n_docs: int) -> None:
+        """Counts known on the host."""
+        k = self._slot()
         if not self.active:
-            self._pending.append((None, None, (int(n_tokens), int(n_docs))))
+            self._pending.append((None, k, (int(n_tokens), int(n_docs))))
             return
+        self._host[k, 0] = int(n_tokens); self._host[k, 1] = int(n_docs)
+        self._send[k].copy_(self._host[k], non_blocking=True)
+        self._post(k)
+
+    def post_device(self) -> None:
+        """Counts already written into `send_ptr()` by work enqueued on the current stream."""
+        k = self._slot()
+        if not self.active:
+            self._pending.append((None, k, None))
+            return
+        self._post(k)
+
+    def _post(self, k: int) -> None:
         import torch.distributed as dist
-        host, mine, gathered = self._buffers()
-        host[0] = int(n_tokens); host[1] = int(n_docs)
-        mine.copy_(host, non_blocking=True)
-        work = dist.all_gather(gathered, mine, async_op=True)
-        self._pending.append((work, (host, mine, gathered), None))
+        work = dist.all_gather_into_tensor(self._recv[k].view(-1), self._send[k], async_op=True)
+        self._pending.append((work, k, None))
 
     def wait(self):
-        import torch
-        work, bufs, local = self._pending.pop(0)
+        work, k, local = self._pending.pop(0)
         if work is None:
-            counts = np.asarray([local], dtype=np.int64)
-            return counts, 0, 0
+            if local is None:
+                local = tuple(int(x) for x in self._send[k].cpu().tolist())
+            return np.asarray([local], dtype=np.int64), 0, 0
         work.wait()
-        counts = torch.stack(bufs[2]).cpu().numpy()
-        self._pool.append(bufs)
+        counts = self._recv[k].cpu().numpy().copy()
         return counts, int(counts[:self.rank, 0].sum()), int(counts[:self.rank, 1].sum())
 
     def drain(self):
@@ -113,3 +130,39 @@ class CountExchange:
         while self._pending:
             out.append(self.wait())
         return out
+
+
+def gpu_numa_cpus(device_index: int) -> list[int] | None:
+    """CPUs of the NUMA node the GPU hangs off (sysfs), or None when the platform does not say."""
+    try:
+        import torch
+        p = torch.cuda.get_device_properties(device_index)
+        bdf = f"{p.pci_domain_id:04x}:{p.pci_bus_id:02x}:{p.pci_device_id:02x}.0"
+        node = int(open(f"/sys/bus/pci/devices/{bdf}/numa_node").read().strip())
+        if node < 0:
+            return None
+        cpus: list[int] = []
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.extend(range(int(a), int(b or a) + 1))
+        return cpus or None
+    except Exception:
+        return None
+
+
+def bind_to_gpu_numa(device_index: int) -> dict:
+    """Pin this process to the CPUs next to its GPU BEFORE it allocates pinned host buffers: first touch then puts
+    them on that node, and H2D / D2H do not cross the inter-socket link (4 ranks sharing one node's memory halved the
+    PCIe rate in round 1).  Returns what was done, for the bench line."""
+    import os
+    cpus = gpu_numa_cpus(device_index)
+    if not cpus:
+        return {"bound": False, "why": "no NUMA information for the device"}
+    try:
+        allowed = sorted(set(cpus) & set(os.sched_getaffinity(0)))
+        if not allowed:
+            return {"bound": False, "why": "node CPUs not in the allowed set"}
+        os.sched_setaffinity(0, allowed)
+        return {"bound": True, "cpus": f"{allowed[0]}-{allowed[-1]} ({len(allowed)})"}
+    except Exception as e:                                     # noqa: BLE001
+        return {"bound": False, "why": str(e)}

@@ -61,6 +61,33 @@ def generate(kind: int, seed: int, nbytes: int) -> np.ndarray:
     return out
 
 
+def generate_range(kind: int, seed: int, nbytes: int, lo: int, hi: int) -> np.ndarray:
+    """Bytes [lo, hi) of generate(kind, seed, nbytes) without producing the rest (english / mixed streams are
+    independent 8 MiB chunks); lo must be a multiple of the chunk size.  Used to shard ONE corpus over ranks."""
+    if kind == CODE or nbytes <= CHUNK:
+        return generate(kind, seed, nbytes)[lo:hi]
+    assert lo % CHUNK == 0
+    out = np.empty(hi - lo, dtype=np.uint8)
+    lib = _lib()
+    from concurrent.futures import ThreadPoolExecutor
+
+    def one(i):
+        a = i * CHUNK
+        n = min(CHUNK, nbytes - a)                     # the chunk as generate() sizes it
+        if a + n <= hi:
+            return lib.corpus_generate(kind, seed * 1000003 + i + 1, n, C.c_void_p(out.ctypes.data + (a - lo)))
+        tmp = np.empty(n, dtype=np.uint8)              # last, partially wanted chunk
+        rc = lib.corpus_generate(kind, seed * 1000003 + i + 1, n, tmp.ctypes.data_as(C.c_void_p))
+        out[a - lo:] = tmp[:hi - a]
+        return rc
+
+    with ThreadPoolExecutor(os.cpu_count() or 1) as ex:
+        rcs = list(ex.map(one, range(lo // CHUNK, (hi + CHUNK - 1) // CHUNK)))
+    if any(rcs):
+        raise ValueError("bad corpus kind")
+    return out
+
+
 def _cut_points(text: np.ndarray, marks: np.ndarray, at_space: bool) -> np.ndarray:
     """Move each mark back to a legal cut: after a space (english) or onto a UTF-8 lead byte."""
     cuts = []
