@@ -351,6 +351,23 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    def rank0_section(tag, fn):
+        """Run fn on rank 0 while the other ranks wait on the HOST (c10d store), not in an NCCL barrier: their GPUs stay
+        idle, which matters when rank 0 drives all of them through the one-process engine."""
+        barrier()
+        if world == 1:
+            fn()
+            return
+        store = dist.distributed_c10d._get_default_store()
+        if rank == 0:
+            try:
+                fn()
+            finally:
+                store.set(f"b200bench_{tag}", "done")
+        else:
+            store.wait([f"b200bench_{tag}"])
+        barrier()
+
     def allmax(x):
         t = torch.tensor([float(x)], dtype=torch.float64, device="cuda")
         if world > 1:
@@ -384,6 +401,12 @@ def main():
         ms_total, n_tok, placements = timed_device_loop(b, steps, world, xchg)
         barrier()
         clocks = sampler.stop() if sampler else None
+        per_rank = [ms_total / steps]
+        if world > 1:                                           # which rank set the pace (the MAX is what counts)
+            t = torch.tensor([ms_total / steps], dtype=torch.float64, device="cuda")
+            g = [torch.zeros_like(t) for _ in range(world)]
+            dist.all_gather(g, t)
+            per_rank = [float(x.item()) for x in g]
         ms_step = allmax(ms_total) / steps
         tot_bytes, tot_tokens = allsum(b.N, n_tok)
         b.step_sync()                                           # one instrumented step for the per-stage events
@@ -394,7 +417,7 @@ def main():
         same = allok(same and e2e_tokens == n_tok)
         return {"parity": bool(same), "value": tot_bytes / (ms_step * 1e-3) / 1e9, "ms_per_step": ms_step,
                 "mtokens_per_s": tot_tokens / (ms_step * 1e-3) / 1e6, "bytes": tot_bytes, "tokens": tot_tokens,
-                "n_tok_rank": n_tok, "stage_ms": {k: v for k, v in tm.items() if k.endswith("_ms")}, "launches": tm["launches"],
+                "n_tok_rank": n_tok, "per_rank_ms_per_step": per_rank, "stage_ms": {k: v for k, v in tm.items() if k.endswith("_ms")}, "launches": tm["launches"],
                 "e2e": {"value": tot_bytes / e2e_s / 1e9, "unit": "GB/s", "h2d_bytes_per_step": int(b.N + 8 * (b.n_docs + 1)),
                         "d2h_bytes_per_step": int(4 * e2e_tokens + 8 * (b.n_docs + 1)), "ms_per_step": e2e_s * 1e3,
                         "mtokens_per_s": tot_tokens / e2e_s / 1e6, "identical_to_device_result": bool(same),
@@ -441,6 +464,7 @@ def main():
         "n_docs_per_gpu": n_docs, "gpu_launches": m["launches"] * args.steps,
         "timing": "K async steps on one CUDA stream, events on that stream, no host sync inside a step; max over ranks",
         "parity": {"oracle_sample_every_rank": True, "e2e_identical_to_device_result": True},
+        "per_rank_ms_per_step": m["per_rank_ms_per_step"],
         "stage_ms": stage, "kernel_ms": kern_ms,
         "roofline": {"bound": "hbm", "kernel": dominant, "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
@@ -456,8 +480,7 @@ def main():
 
     # ---- the calls a tiktoken user makes (host marshalling inside the timed region), rank 0 only
     if not args.no_extras and args.workload == "config2":
-        barrier()
-        if rank == 0:
+        def api_section():
             try:
                 api = {}
                 k = int(np.searchsorted(b.off, min(N, 256 << 20), side="right")) - 1
@@ -494,7 +517,7 @@ def main():
                 line["api"] = api
             except Exception as e:                                   # noqa: BLE001
                 line["api"] = {"error": repr(e)}
-        barrier()
+        rank0_section("api", api_section)
 
     if args.decode and world == 1:
         h_text_np, h_off_np = b.h_text.numpy()[:N], b.h_off.numpy().view(np.uint64)
@@ -570,8 +593,7 @@ def main():
 
     # ---- ONE process driving every GPU of the job through the same C ABI (b200bpe_create_multi): rank 0, the others idle
     if not args.no_extras and args.workload == "config2" and world > 1 and not args.bytes:
-        barrier()
-        if rank == 0:
+        def multi_section():
             try:
                 import tiktoken_b200
                 pat, ranks, special, _ = vu.load_encoding("cl100k_base")
@@ -597,7 +619,7 @@ def main():
                 del encm, single
             except Exception as e:                                   # noqa: BLE001
                 line["one_process_multi_gpu"] = {"error": repr(e)}
-        barrier()
+        rank0_section("multi", multi_section)
 
     if rank == 0:
         print(json.dumps(line))

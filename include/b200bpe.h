@@ -61,6 +61,10 @@ int b200bpe_create_multi(const uint8_t *tok_bytes, const uint64_t *tok_off, cons
 /* Number of devices an engine runs on. */
 int b200bpe_n_devices(b200bpe_t *h);
 
+/* Release the grow-only device work-spaces (~25 bytes per input byte of the largest batch seen, per pipeline slot)
+ * and the pooled pinned result blocks; the tables stay and the next call re-allocates what it needs. */
+int b200bpe_trim(b200bpe_t *h);
+
 /* Outstanding results keep the engine alive: with results not yet freed this only marks the handle dead and the
  * last b200bpe_result_free tears it down (TiktokenBuffer owns its Vec in the reference, src/py.rs:186-189). */
 void b200bpe_destroy(b200bpe_t *h);

@@ -341,3 +341,16 @@ def test_one_process_multi_gpu_engine():
     small, soff = corpus.config4(n_docs=50_000, seed=3)
     exp_t, exp_o = o.encode_ordinary_batch_np(small, soff, CORES)
     assert _same(e.encode_ordinary_packed(small, soff), exp_t, exp_o)
+
+
+def test_trim_releases_and_the_engine_keeps_working():
+    import tiktoken_b200
+    pat, ranks, special, _ = vu.load_encoding("p50k_base", allow_real=False)
+    e = tiktoken_b200.Encoding("trim", pat_str=pat, mergeable_ranks=ranks, special_tokens=special)
+    o = _oracle(ranks, special, pat)
+    text, off = corpus.config5(nbytes=3 << 20, seed=11)
+    exp_t, exp_o = o.encode_ordinary_batch_np(text, off, 1)
+    assert _same(e.encode_ordinary_packed(text, off), exp_t, exp_o)
+    e._core_bpe.trim()                                   # work-spaces and pooled pinned blocks are gone, tables stay
+    assert _same(e.encode_ordinary_packed(text, off), exp_t, exp_o)
+    assert e.decode_bytes(exp_t) == text.tobytes()

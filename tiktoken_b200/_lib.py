@@ -56,6 +56,8 @@ def lib() -> C.CDLL:
     L.b200bpe_create.argtypes = [vp, vp, vp, u32, vp, vp, vp, u32, C.c_char_p, i32, C.POINTER(vp)]
     L.b200bpe_create_multi.restype = i32
     L.b200bpe_create_multi.argtypes = [vp, vp, vp, u32, vp, vp, vp, u32, C.c_char_p, vp, i32, C.POINTER(vp)]
+    L.b200bpe_trim.restype = i32
+    L.b200bpe_trim.argtypes = [vp]
     L.b200bpe_n_devices.restype = i32
     L.b200bpe_n_devices.argtypes = [vp]
     L.b200bpe_encode_batch_special.restype = i32
@@ -108,7 +110,7 @@ EXPORTS = [
     "b200bpe_result_offsets", "b200bpe_result_n_tokens", "b200bpe_result_n_docs", "b200bpe_result_free",
     "b200bpe_decode_bytes", "b200bpe_decode_batch", "b200bpe_last_timings", "b200bpe_table_bytes", "b200bpe_last_error",
     "b200bpe_version", "b200bpe_device_count", "b200bpe_create_multi", "b200bpe_n_devices", "b200bpe_encode_batch_special",
-    "b200bpe_special_name", "b200bpe_encode_device_async", "b200bpe_device_wait",
+    "b200bpe_special_name", "b200bpe_encode_device_async", "b200bpe_device_wait", "b200bpe_trim",
 ]
 
 

@@ -346,6 +346,10 @@ class CoreBPE:
         d["launches"] = int(n.value)
         return d
 
+    def trim(self) -> None:
+        """Give the engine's grow-only device work-spaces and pooled pinned blocks back (tables stay)."""
+        _lib.check(self._L.b200bpe_trim(self._h))
+
     def table_bytes(self) -> dict:
         b = (C.c_uint64 * 4)()
         self._L.b200bpe_table_bytes(self._h, b)

@@ -128,18 +128,21 @@ void parallel_memcpy(void *dst, const void *src, size_t n, int threads) {
 // three slots in flight per device (H2D of chunk c+1, kernels of chunk c, D2H of chunk c-1).
 struct Slot {
     DevBuf<uint8_t> w_text; DevBuf<unsigned long long> w_docoff, w_tokoff, w_sub_base;
-    DevBuf<uint32_t> w_ptok, w_mres, w_mq_pos, w_mq_roff, w_sub_count; DevBuf<uint8_t> w_mq_len, w_mq_cnt;
+    DevBuf<uint32_t> w_ptok, w_mres, w_mq_pos, w_mq_roff, w_mq_dst, w_doc_tiles, w_sub_count; DevBuf<uint8_t> w_mq_len, w_mq_cnt;
     DevBuf<uint4> w_mq_key, w_mq_skey, w_mq_smeta;
-    DevBuf<uint32_t> w_dbits, w_pbits, w_psum, w_sfd, w_lidx, w_out, w_ltok, w_hbits, w_ibits, w_sbits, w_cbits;
+    DevBuf<uint32_t> w_dbits, w_pbits, w_psum, w_sfd, w_lidx, w_out, w_ltok, w_hbits, w_ibits, w_sbits, w_cbits, w_slow;
     DevBuf<unsigned long long> w_lq_start, w_lq_off; DevBuf<unsigned int> w_lq_len, w_lq_ntok, w_lq_cls, w_big_n, w_sort_hist;
     DevBuf<unsigned long long> w_big_dst, w_big_src, w_scan_part;
     DevBuf<uint32_t> w_idA, w_rkA, w_idB, w_rkB, w_aux1, w_aux2; DevBuf<uint8_t> w_flag, w_spflags;
     size_t long_cap = 0;            // entries of the global merge scratch (pieces > 256 bytes), grown on ERR_LONGCAP
     size_t miss_cap = 0, mres_cap = 0;   // miss queue entries / miss result tokens, grown on ERR_MISSCAP
+    size_t slow_cap = 0;            // positions left to the general pre-tokeniser rule function, grown on ERR_SLOWCAP
     Counters *d_ctr = nullptr; Counters *h_ctr = nullptr;   // h_ctr pinned
     unsigned int *d_sticky = nullptr;                       // error bits of every pipeline since the last wait
     cudaStream_t stream = nullptr;
-    static const int N_EV = 10;
+    cudaStream_t side = nullptr;     // the group kernels (17..1024 bytes) run here, next to probe + miss on the main stream,
+    cudaStream_t side2 = nullptr;    // and the scratch kernels (warp / block / cluster per piece: a few SMs each) here
+    static const int N_EV = 14;       // [10] fork, [11] side start, [12] side end (join), [13] side2 end (join)
     cudaEvent_t ev[N_EV];
     PinnedBuf stage;                // pinned staging for callers whose text is pageable memory
     float last_ms[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
@@ -152,26 +155,35 @@ struct Slot {
         if (e == cudaSuccess) e = cudaMemset(d_sticky, 0, 16);
         if (e == cudaSuccess) e = cudaHostAlloc((void **)&h_ctr, sizeof(Counters), cudaHostAllocPortable);
         if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking);
+        if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking);
+        if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&side2, cudaStreamNonBlocking);
         for (int i = 0; i < N_EV && e == cudaSuccess; i++) e = cudaEventCreate(&ev[i]);
         ok = (e == cudaSuccess);
         return e;
     }
-    void destroy() {
+    void release_workspace() {
         w_text.release(); w_docoff.release(); w_tokoff.release(); w_sub_base.release();
-        w_ptok.release(); w_mres.release(); w_mq_pos.release(); w_mq_roff.release(); w_sub_count.release();
+        w_ptok.release(); w_mres.release(); w_mq_pos.release(); w_mq_roff.release(); w_mq_dst.release(); w_doc_tiles.release(); w_sub_count.release();
         w_mq_len.release(); w_mq_cnt.release(); w_mq_key.release(); w_mq_skey.release(); w_mq_smeta.release();
         w_dbits.release(); w_pbits.release(); w_psum.release(); w_sfd.release(); w_lidx.release(); w_out.release(); w_ltok.release();
-        w_hbits.release(); w_ibits.release(); w_sbits.release(); w_cbits.release(); w_spflags.release();
+        w_hbits.release(); w_ibits.release(); w_sbits.release(); w_cbits.release(); w_slow.release(); w_spflags.release();
         w_lq_start.release(); w_lq_off.release(); w_lq_len.release(); w_lq_ntok.release(); w_lq_cls.release(); w_big_n.release();
         w_sort_hist.release(); w_big_dst.release(); w_big_src.release(); w_scan_part.release();
         w_idA.release(); w_rkA.release(); w_idB.release(); w_rkB.release(); w_aux1.release(); w_aux2.release();
         w_flag.release();
+        if (stage.p) cudaFreeHost(stage.p);
+        stage.p = nullptr; stage.cap = 0;
+        long_cap = miss_cap = mres_cap = slow_cap = 0;
+    }
+    void destroy() {
+        release_workspace();
         if (d_ctr) cudaFree(d_ctr);
         if (d_sticky) cudaFree(d_sticky);
         if (h_ctr) cudaFreeHost(h_ctr);
-        if (stage.p) cudaFreeHost(stage.p);
         if (ok) { for (int i = 0; i < N_EV; i++) cudaEventDestroy(ev[i]); }
         if (stream) cudaStreamDestroy(stream);
+        if (side) cudaStreamDestroy(side);
+        if (side2) cudaStreamDestroy(side2);
     }
 };
 
@@ -218,7 +230,7 @@ struct b200bpe {
     uint32_t last_launches = 0;
     size_t chunk_bytes = 64u << 20; bool chunk_forced = false;
     int copy_threads = 4;
-    bool mid_group = true;           // 17..256-byte pieces: group-of-lanes kernel (needs ranks < 2^24)
+    bool mid_group = true;           // 17..1024-byte pieces: group-of-lanes kernels (need ranks < 2^22)
     std::mutex mu;
     std::vector<PinnedBuf> pinned_pool;
     // results keep the engine alive: b200bpe_destroy with results outstanding only marks the handle dead, the last
@@ -372,7 +384,7 @@ extern "C" int b200bpe_create_multi(const uint8_t *tok_bytes, const uint64_t *to
     DeviceGuard guard;
     b200bpe *h = new b200bpe();
     h->pattern = pattern;
-    int rc = build_tables(tok_bytes, tok_off, tok_rank, n_tok, h->H);
+    int rc = build_tables(tok_bytes, tok_off, tok_rank, n_tok, h->H, (uint32_t)env_long("B200BPE_PAIR_SLACK", 3, 2, 16));
     if (rc) { std::string m = h->H.error; delete h; return fail(rc == -3 ? B200BPE_EDUPRANK : B200BPE_EINVAL, m); }
     for (uint32_t i = 0; i < n_sp; i++) {
         std::string s((const char *)sp_bytes + sp_off[i], (size_t)(sp_off[i + 1] - sp_off[i]));
@@ -441,6 +453,27 @@ extern "C" void b200bpe_destroy(b200bpe_t *h) {
 
 extern "C" int b200bpe_n_devices(b200bpe_t *h) { return h ? (int)h->devs.size() : 0; }
 
+// Give the grow-only work-spaces (about 25 bytes of device memory per input byte of the largest batch seen, per pipeline
+// slot) and the pooled pinned result blocks back; the tables stay.  The next call re-allocates what it needs.
+extern "C" int b200bpe_trim(b200bpe_t *h) {
+    if (!h) return fail(B200BPE_EINVAL, "null handle");
+    std::lock_guard<std::mutex> lk(h->mu);
+    if (h->pending.active) return fail(B200BPE_EINVAL, "a device call is in flight: b200bpe_device_wait first");
+    DeviceGuard guard;
+    for (auto *D : h->devs) {
+        CUDA_TRY(cudaSetDevice(D->device));
+        for (int i = 0; i < DevCtx::N_SLOTS; i++) {
+            CUDA_TRY(cudaStreamSynchronize(D->slots[i].stream));
+            CUDA_TRY(cudaStreamSynchronize(D->slots[i].side));
+            CUDA_TRY(cudaStreamSynchronize(D->slots[i].side2));
+            D->slots[i].release_workspace();
+        }
+    }
+    for (auto &b : h->pinned_pool) cudaFreeHost(b.p);
+    h->pinned_pool.clear();
+    return B200BPE_OK;
+}
+
 // --------------------------------------------------------------------------------------------
 // the device pipeline
 // --------------------------------------------------------------------------------------------
@@ -480,11 +513,16 @@ static int enqueue_pipeline(b200bpe *h, DevCtx *D, Slot &S, const PipeArgs &a) {
         if (S.miss_cap < want_q) S.miss_cap = want_q;
         if (S.mres_cap < want_r) S.mres_cap = want_r;
         const size_t mcap = S.miss_cap;
-        CUDA_TRY(S.w_mq_pos.ensure(mcap)); CUDA_TRY(S.w_mq_roff.ensure(mcap));
+        CUDA_TRY(S.w_mq_pos.ensure(mcap)); CUDA_TRY(S.w_mq_roff.ensure(mcap)); CUDA_TRY(S.w_mq_dst.ensure(mcap));
         CUDA_TRY(S.w_mq_len.ensure(mcap)); CUDA_TRY(S.w_mq_cnt.ensure(mcap));
         CUDA_TRY(S.w_mq_key.ensure(mcap)); CUDA_TRY(S.w_mq_skey.ensure(mcap)); CUDA_TRY(S.w_mq_smeta.ensure(mcap));
         CUDA_TRY(S.w_mres.ensure(S.mres_cap + 64));
         CUDA_TRY(S.w_sort_hist.ensure((size_t)SORT_BLOCKS * 17 + 32));
+    }
+    {   // undecided pre-tokeniser positions: under 2 % on the worst corpus seen; sized for 12 %, grown on ERR_SLOWCAP
+        const size_t want = std::max<size_t>((size_t)(n_bytes / 8) + 4096, MISS_CAP_MIN);
+        if (S.slow_cap < want) S.slow_cap = want;
+        CUDA_TRY(S.w_slow.ensure(S.slow_cap));
     }
     CUDA_TRY(S.w_lidx.ensure((size_t)(n_bytes >> 4) + 4));
     CUDA_TRY(S.w_ltok.ensure((size_t)n_bytes + 4));
@@ -493,7 +531,7 @@ static int enqueue_pipeline(b200bpe *h, DevCtx *D, Slot &S, const PipeArgs &a) {
     CUDA_TRY(S.w_lq_len.ensure(qcap)); CUDA_TRY(S.w_lq_ntok.ensure(qcap));
     size_t cls_cap[N_CLS], cls_total = 0;                          // per-class index lists, back to back
     {
-        const size_t min_len[N_CLS] = {SHORT_MAX + 1, 33, 65, 129, 257, BLOCK_MIN + 1, CLUSTER_MIN + 1};
+        const size_t min_len[N_CLS] = {SHORT_MAX + 1, 33, 65, 129, 257, GROUP_MAX + 1, BLOCK_MIN + 1, CLUSTER_MIN + 1};
         for (int c = 0; c < N_CLS; c++) { cls_cap[c] = (size_t)(n_bytes / min_len[c]) + 4; cls_total += cls_cap[c]; }
     }
     CUDA_TRY(S.w_lq_cls.ensure(cls_total));
@@ -508,17 +546,24 @@ static int enqueue_pipeline(b200bpe *h, DevCtx *D, Slot &S, const PipeArgs &a) {
     }
     LongQ q;
     q.start = S.w_lq_start.p; q.len = S.w_lq_len.p; q.off = S.w_lq_off.p; q.ntok = S.w_lq_ntok.p; q.scratch_cap = S.long_cap;
+    q.sub_count = S.w_sub_count.p;
     { size_t o = 0; for (int c = 0; c < N_CLS; c++) { q.cls[c] = S.w_lq_cls.p + o; o += cls_cap[c]; } }
+    // documents are sparse when fewer than one sub-tile in four can hold a document start: the gather then takes the
+    // doc-start sub-tiles from a list instead of giving every sub-tile the shared memory their bookkeeping needs
+    const bool sparse_docs = (n_docs + 1) * 4 < (uint64_t)n_tiles;
+    if (sparse_docs) CUDA_TRY(S.w_doc_tiles.ensure((size_t)n_docs + 8));
     uint32_t launches = 0;
 
     CUDA_TRY(cudaEventRecord(S.ev[0], st));
     CUDA_TRY(cudaMemsetAsync(S.d_ctr, 0, sizeof(Counters), st));
     CUDA_TRY(cudaMemsetAsync(S.w_dbits.p, 0, ((size_t)n_words + 8) * 4, st));
     CUDA_TRY(cudaMemsetAsync(S.w_sfd.p, 0xFF, ((size_t)n_words + 4) * 4, st));
+    CUDA_TRY(cudaMemsetAsync(S.w_sub_count.p, 0, ((size_t)n_tiles + 2) * 4, st));
     CUDA_TRY(cudaMemsetAsync(S.w_pbits.p + n_words, 0, (pb_words - (size_t)n_words) * 4, st));
     {
         unsigned long long nd1 = n_docs + 1;
-        mark_docs_kernel<<<(unsigned)((nd1 + 255) / 256), 256, 0, st>>>(a.d_doc_off, n_docs, n_bytes, S.w_dbits.p, S.w_sfd.p, S.d_ctr);
+        mark_docs_kernel<<<(unsigned)((nd1 + 255) / 256), 256, 0, st>>>(a.d_doc_off, n_docs, n_bytes, S.w_dbits.p, S.w_sfd.p,
+                                                                       sparse_docs ? S.w_doc_tiles.p : nullptr, S.d_ctr);
         launches++;
     }
     // ---- special tokens (CoreBPE::encode, lib.rs:375-442; disallowed check, core.py:120-124) ------------------
@@ -544,26 +589,45 @@ static int enqueue_pipeline(b200bpe *h, DevCtx *D, Slot &S, const PipeArgs &a) {
     {
         unsigned grid = (unsigned)((n_words + 255) / 256);
         if (a.single_piece) single_piece_bits_kernel<<<grid, 256, 0, st>>>(S.w_pbits.p, S.w_psum.p, (long long)n_bytes, n_words);
-        else if (h->pattern == PAT_R50K)
-            pretok_kernel<PAT_R50K><<<grid, 256, 0, st>>>(a.d_text, (long long)n_bytes, hbits, D->uc, S.w_pbits.p, S.w_psum.p, n_words, ibits);
-        else if (h->pattern == PAT_CL100K)
-            pretok_kernel<PAT_CL100K><<<grid, 256, 0, st>>>(a.d_text, (long long)n_bytes, hbits, D->uc, S.w_pbits.p, S.w_psum.p, n_words, ibits);
-        else
-            pretok_kernel<PAT_O200K><<<grid, 256, 0, st>>>(a.d_text, (long long)n_bytes, hbits, D->uc, S.w_pbits.p, S.w_psum.p, n_words, ibits);
+        else {
+            const uint32_t scap = (uint32_t)std::min<size_t>(S.slow_cap, 0xFFFFFFF0u);
+#define B2_PRETOK(P)                                                                                                                   \
+    pretok_kernel<P><<<grid, 256, 0, st>>>(a.d_text, (long long)n_bytes, hbits, D->uc, S.w_pbits.p, S.w_psum.p, n_words, ibits,          \
+                                          S.w_slow.p, scap, S.d_ctr);                                                                  \
+    pretok_slow_kernel<P><<<148 * 8, 256, 0, st>>>(a.d_text, (long long)n_bytes, hbits, D->uc, S.w_pbits.p, S.w_psum.p, S.w_slow.p, scap, S.d_ctr)
+            if (h->pattern == PAT_R50K) { B2_PRETOK(PAT_R50K); }
+            else if (h->pattern == PAT_CL100K) { B2_PRETOK(PAT_CL100K); }
+            else { B2_PRETOK(PAT_O200K); }
+#undef B2_PRETOK
+            launches++;
+        }
         launches++;
     }
     CUDA_TRY(cudaEventRecord(S.ev[2], st));
     {
         unsigned grid = (unsigned)((n_words + 255) / 256);
         find_long_kernel<<<grid, 256, 0, st>>>(S.w_pbits.p, S.w_psum.p, (long long)n_bytes, n_words, q, S.w_lidx.p, sbits, S.d_ctr);
-        if (h->mid_group)        // a group of lanes per piece, 4 KiB of state per warp: 12 blocks of 4 warps per SM
-            mid_group_kernel<<<148 * 12, MIDG_WARPS * 32, 0, st>>>(a.d_text, D->T, q, S.w_ltok.p, S.d_ctr);
-        else                     // ranks of 2^24 and above: one piece per lane, 72 KiB of columns per block
-            mid_thread_kernel<<<148 * 3, MID_WARPS * 32, MID_SMEM_BYTES, st>>>(a.d_text, D->T, q, S.w_ltok.p, S.d_ctr);
+        launches++;
+        // The long-piece kernels only depend on find_long and nothing before the scan depends on them: they run on a
+        // side stream next to probe + miss sort + miss (few SMs are busy with a giant piece, the rest probe).
+        cudaStream_t ls = S.side, ls2 = S.side2;
+        CUDA_TRY(cudaEventRecord(S.ev[10], st));
+        CUDA_TRY(cudaStreamWaitEvent(ls, S.ev[10], 0));
+        CUDA_TRY(cudaStreamWaitEvent(ls2, S.ev[10], 0));
+        CUDA_TRY(cudaEventRecord(S.ev[11], ls));
         LongScratch LS{S.w_idA.p, S.w_rkA.p, S.w_idB.p, S.w_rkB.p, S.w_aux1.p, S.w_aux2.p, S.w_flag.p};
-        long_piece_kernel<<<148 * 8, LONG_WARPS * 32, 0, st>>>(a.d_text, D->T, q, LS, S.w_ltok.p, S.d_ctr);
-        giant_piece_kernel<<<148, GIANT_THREADS, 0, st>>>(a.d_text, D->T, q, LS, S.w_ltok.p, S.d_ctr);
-        cluster_piece_kernel<<<(148 / CLUSTER_CTAS) * CLUSTER_CTAS, GIANT_THREADS, 0, st>>>(a.d_text, D->T, q, LS, S.w_ltok.p, S.d_ctr);
+        if (h->mid_group) {      // 17..1024 bytes: a group of lanes per piece, state in shared memory
+            mid_group32_kernel<<<148 * 4, MIDG_WARPS * 32, 0, ls>>>(a.d_text, D->T, q, S.w_ltok.p, S.d_ctr);
+            mid_group16_kernel<<<148 * 9, MIDG_WARPS * 32, 0, ls>>>(a.d_text, D->T, q, S.w_ltok.p, S.d_ctr);
+        } else {                 // ranks of 2^22 and above: one piece per lane (72 KiB of columns per block) / warp per piece
+            mid_thread_kernel<<<148 * 3, MID_WARPS * 32, MID_SMEM_BYTES, ls>>>(a.d_text, D->T, q, S.w_ltok.p, S.d_ctr);
+            long_piece_kernel<<<148 * 8, LONG_WARPS * 32, 0, ls>>>(a.d_text, D->T, q, LS, S.w_ltok.p, S.d_ctr, CLS_G1024);
+        }
+        long_piece_kernel<<<148 * 8, LONG_WARPS * 32, 0, ls2>>>(a.d_text, D->T, q, LS, S.w_ltok.p, S.d_ctr, CLS_WARP);
+        giant_piece_kernel<<<148, GIANT_THREADS, 0, ls2>>>(a.d_text, D->T, q, LS, S.w_ltok.p, S.d_ctr);
+        cluster_piece_kernel<<<(148 / CLUSTER_CTAS) * CLUSTER_CTAS, GIANT_THREADS, 0, ls2>>>(a.d_text, D->T, q, LS, S.w_ltok.p, S.d_ctr);
+        CUDA_TRY(cudaEventRecord(S.ev[13], ls2));
+        CUDA_TRY(cudaEventRecord(S.ev[12], ls));
         launches += 5;
     }
     CUDA_TRY(cudaEventRecord(S.ev[3], st));
@@ -574,6 +638,7 @@ static int enqueue_pipeline(b200bpe *h, DevCtx *D, Slot &S, const PipeArgs &a) {
         p.doc_off = a.d_doc_off; p.n_docs = n_docs; p.q = q; p.lidx = S.w_lidx.p; p.ltok = S.w_ltok.p;
         p.ptok = S.w_ptok.p; p.mres = S.w_mres.p; p.sbits = sbits;
         p.mq.key = S.w_mq_key.p; p.mq.pos = S.w_mq_pos.p; p.mq.roff = S.w_mq_roff.p; p.mq.len = S.w_mq_len.p; p.mq.cnt = S.w_mq_cnt.p;
+        p.mq.dst = S.w_mq_dst.p; p.doc_tiles = S.w_doc_tiles.p;
         p.mq.skey = S.w_mq_skey.p; p.mq.smeta = S.w_mq_smeta.p; p.mq.cap = (uint32_t)std::min<size_t>(S.miss_cap, 0xFFFFFFF0u);
         p.mq.mres_cap = S.mres_cap;
         p.sub_count = S.w_sub_count.p; p.sub_base = S.w_sub_base.p;
@@ -588,17 +653,23 @@ static int enqueue_pipeline(b200bpe *h, DevCtx *D, Slot &S, const PipeArgs &a) {
         miss_scatter_kernel<<<SORT_BLOCKS, 256, 0, st>>>(p, S.w_sort_hist.p);
         miss_kernel<<<148 * 16, MISS_WARPS * 32, 0, st>>>(p, D->T);
         CUDA_TRY(cudaEventRecord(S.ev[7], st));
+        CUDA_TRY(cudaStreamWaitEvent(st, S.ev[12], 0));          // join: the long pieces' tokens and counts are needed from here on
+        CUDA_TRY(cudaStreamWaitEvent(st, S.ev[13], 0));
         {
             const long long nb = (n_tiles + SCAN_ITEMS - 1) / SCAN_ITEMS;
             scan_partial_kernel<<<(unsigned)nb, 256, 0, st>>>(S.w_sub_count.p, n_tiles, S.w_scan_part.p);
             scan_top_kernel<<<1, 1024, 0, st>>>(S.w_scan_part.p, nb, S.d_ctr);
             scan_final_kernel<<<(unsigned)nb, 256, 0, st>>>(S.w_sub_count.p, n_tiles, S.w_scan_part.p, S.w_sub_base.p, S.d_ctr);
         }
-        gather_kernel<false><<<(unsigned)((n_tiles + GATHER_WARPS - 1) / GATHER_WARPS), GATHER_WARPS * 32, 0, st>>>(p);
-        gather_kernel<true><<<(unsigned)((n_tiles + GATHER_WARPS - 1) / GATHER_WARPS), GATHER_WARPS * 32, 0, st>>>(p);
+        const unsigned gather_grid = (unsigned)((n_tiles + GATHER_WARPS - 1) / GATHER_WARPS);
+        if (sparse_docs) {
+            gather_kernel<0><<<gather_grid, GATHER_WARPS * 32, 0, st>>>(p);
+            gather_kernel<1><<<(unsigned)((n_docs + 1 + GATHER_WARPS - 1) / GATHER_WARPS), GATHER_WARPS * 32, 0, st>>>(p);
+        } else gather_kernel<2><<<gather_grid, GATHER_WARPS * 32, 0, st>>>(p);
+        miss_copy_kernel<<<148 * 8, 256, 0, st>>>(p);
         big_copy_kernel<<<148 * 2, 256, 0, st>>>(p);
         finalize_kernel<<<1, 32, 0, st>>>(S.d_ctr, S.d_sticky, a.d_counts, n_docs);
-        launches += 12;
+        launches += sparse_docs ? 13 : 12;
     }
     CUDA_TRY(cudaEventRecord(S.ev[4], st));
     CUDA_TRY(cudaMemcpyAsync(S.h_ctr, S.d_ctr, sizeof(Counters), cudaMemcpyDeviceToHost, st));
@@ -617,7 +688,7 @@ static int collect_pipeline(b200bpe *h, Slot &S, int *special_idx, uint64_t *spe
     CUDA_TRY(cudaGetLastError());
     cudaEventElapsedTime(&S.last_ms[0], S.ev[0], S.ev[1]);
     cudaEventElapsedTime(&S.last_ms[1], S.ev[1], S.ev[2]);
-    cudaEventElapsedTime(&S.last_ms[2], S.ev[2], S.ev[3]);
+    cudaEventElapsedTime(&S.last_ms[2], S.ev[11], S.ev[12]);     // long-piece kernels (side stream, overlapped with [3])
     cudaEventElapsedTime(&S.last_ms[3], S.ev[3], S.ev[7]);
     cudaEventElapsedTime(&S.last_ms[7], S.ev[7], S.ev[4]);
     cudaEventElapsedTime(&S.last_ms[8], S.ev[3], S.ev[8]);
@@ -631,7 +702,8 @@ static int collect_pipeline(b200bpe *h, Slot &S, int *special_idx, uint64_t *spe
         if (special_pos) *special_pos = packed >> 16;
         return fail(B200BPE_ESPECIAL, "text contains a disallowed special token");
     }
-    if (c.err & (ERR_LONGCAP | ERR_MISSCAP)) {
+    if (c.err & (ERR_LONGCAP | ERR_MISSCAP | ERR_SLOWCAP)) {
+        if (c.err & ERR_SLOWCAP) S.slow_cap = (size_t)c.n_slow + (size_t)(c.n_slow / 8) + 4096;
         if (c.err & ERR_LONGCAP) S.long_cap = (size_t)c.long_bytes + (size_t)(c.long_bytes / 8) + 4096;
         if (c.err & ERR_MISSCAP) {
             S.miss_cap = std::max(S.miss_cap, (size_t)c.n_miss + (size_t)(c.n_miss / 8) + 4096);
@@ -720,7 +792,7 @@ extern "C" int b200bpe_device_wait(b200bpe_t *h, uint64_t *n_tokens) {
     if (rc == B200BPE_RETRY) return fail(B200BPE_ECUDA, "work-space sizing did not converge");
     if (rc) return rc;
     if (c.queued > 1) {
-        if (reran || (sticky & (ERR_LONGCAP | ERR_MISSCAP)))
+        if (reran || (sticky & (ERR_LONGCAP | ERR_MISSCAP | ERR_SLOWCAP)))
             return fail(B200BPE_ECAPACITY, "a work-space had to grow while several device calls were queued: only the last "
                                            "one was re-run, re-issue the others");
         if (sticky & ERR_NOBYTE) return fail(B200BPE_ENOBYTE, "a piece needs a single-byte token that mergeable_ranks does not contain");

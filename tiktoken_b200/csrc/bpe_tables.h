@@ -57,7 +57,7 @@ inline uint64_t long_hash_bytes(const uint8_t *p, uint32_t len) {
 
 // returns 0 or a negative B200BPE_E* code (values mirrored from include/b200bpe.h)
 inline int build_tables(const uint8_t *tok_bytes, const uint64_t *tok_off, const uint32_t *tok_rank,
-                        uint32_t n, HostTables &H) {
+                        uint32_t n, HostTables &H, uint32_t pair_slack = 3) {
     std::unordered_map<std::string, uint32_t> enc;
     enc.reserve((size_t)n * 2 + 16);
     H.decoder.reserve((size_t)n * 2 + 16);
@@ -101,7 +101,7 @@ inline int build_tables(const uint8_t *tok_bytes, const uint64_t *tok_off, const
     }
     H.n_pairs = pairs.size();
     // buckets of two slots; capacity >= 3x the entries
-    uint32_t nbuckets = pow2_at_least(((uint64_t)pairs.size() * 3 + 2) / 2 + 1);
+    uint32_t nbuckets = pow2_at_least(((uint64_t)pairs.size() * pair_slack + 2) / 2 + 1);
     H.pair_mask = nbuckets - 1;
     H.pair_tab.assign((size_t)nbuckets * 2, U4{0xFFFFFFFFu, 0xFFFFFFFFu, RANK_MAX, 0});
     for (auto &p : pairs) {

@@ -14,12 +14,13 @@ static const uint32_t ERR_DOCOFF = 2u;      // malformed document offsets
 static const uint32_t ERR_BADTOKEN = 4u;    // decode: unknown token id
 static const uint32_t ERR_LONGCAP = 8u;     // long-piece merge scratch too small for this batch  -> host grows it and re-runs
 static const uint32_t ERR_MISSCAP = 16u;    // miss queue / miss result space too small            -> host grows it and re-runs
+static const uint32_t ERR_SLOWCAP = 64u;    // list of positions for the general rule function too small               -> host grows it and re-runs
 static const uint32_t ERR_SPECIAL = 32u;    // a disallowed special token occurs in the text (tiktoken/core.py:120-124)
 
 struct UcTables { const uint16_t *stage1; const uint8_t *stage2; const uint8_t *ascii; };
 
-static const int N_CLS = 7;                  // length classes of pieces longer than SHORT_MAX (see LongQ::cls)
-static const int CLS_WARP = 4, CLS_BLOCK = 5, CLS_CLUSTER = 6;
+static const int N_CLS = 8;                  // length classes of pieces longer than SHORT_MAX (see LongQ::cls)
+static const int CLS_G1024 = 4, CLS_WARP = 5, CLS_BLOCK = 6, CLS_CLUSTER = 7;
 
 struct Counters {            // device-resident, zeroed per call; copied to pinned host memory at the end of a pipeline
     unsigned long long long_bytes;   // bytes of pieces that merge in the global scratch (exact, even past the capacity)
@@ -27,16 +28,19 @@ struct Counters {            // device-resident, zeroed per call; copied to pinn
     unsigned long long total_tokens;
     unsigned long long special_pos;  // byte offset of the first disallowed special (ERR_SPECIAL)
     unsigned int n_long;
-    unsigned int n_cls[8];           // long pieces per length class
-    unsigned int cls_head[8];        // work-queue heads of the per-class kernels
+    unsigned int n_cls[10];          // long pieces per length class ([N_CLS]: pieces that did not fit the merge scratch)
+    unsigned int cls_head[10];       // work-queue heads of the per-class kernels
     unsigned int n_big;
     unsigned int n_miss;             // exact, even past the capacity
     unsigned int n_cut;              // allowed-special occurrences found by the device scan
+    unsigned int n_doc_tiles;        // sub-tiles that contain a document start (sparse-document batches)
+    unsigned int n_slow;             // positions left to the general rule function (exact, even past the capacity)
     unsigned int special_idx;        // which disallowed special (ERR_SPECIAL)
     unsigned int ticket;
     unsigned int err;
 };
 
+static const uint32_t GROUP_MAX = 1024;       // pieces up to this length merge in shared memory, a group of lanes per piece
 static const uint32_t BLOCK_MIN = 4096;       // pieces longer than this get a whole block
 static const uint32_t CLUSTER_MIN = 32768;    // pieces longer than this get a thread-block cluster (8 x 1024 threads)
 static const uint32_t LONG_SCRATCH_MIN = 256; // pieces longer than this merge in global scratch (warp / block / cluster per piece)
@@ -46,11 +50,19 @@ struct LongQ {               // queue of pieces longer than SHORT_MAX bytes
     unsigned int *len;
     unsigned long long *off;     // offset of its region in the global merge scratch (pieces > LONG_SCRATCH_MIN only)
     unsigned int *ntok;
-    // indices (into this queue) per length class: 0: 17..32, 1: 33..64, 2: 65..128, 3: 129..256 bytes (one piece per
-    // lane), 4: 257..BLOCK_MIN (warp per piece), 5: ..CLUSTER_MIN (block per piece), 6: longer (cluster per piece)
+    // indices (into this queue) per length class: 0: 17..32, 1: 33..64, 2: 65..128, 3: 129..256, 4: 257..GROUP_MAX bytes
+    // (a group of lanes per piece), 5: ..BLOCK_MIN (warp per piece, global scratch), 6: ..CLUSTER_MIN (block per piece),
+    // 7: longer (cluster per piece)
     unsigned int *cls[N_CLS];
     unsigned long long scratch_cap;   // capacity (entries) of the global merge scratch
+    uint32_t *sub_count;              // tokens per 1 KiB sub-tile: a finished piece credits its tokens to the sub-tile of its start
 };
+
+// a long piece is done: publish its token count (the gather reads ntok, the scan reads sub_count)
+__device__ __forceinline__ void long_piece_done(const LongQ &q, unsigned int qi, uint32_t nt) {
+    q.ntok[qi] = nt;
+    atomicAdd(q.sub_count + (q.start[qi] >> 10), nt);
+}
 
 struct LongScratch {
     uint32_t *idA, *rkA, *idB, *rkB, *aux1, *aux2;

@@ -27,6 +27,7 @@ struct MissQ {                // queue of pieces (2..16 bytes) that are not toke
     uint32_t *roff;           // offset of its result region in mres (sum of lengths => tokens always fit)
     uint8_t *len;
     uint8_t *cnt;             // tokens produced (written by miss_kernel)
+    uint32_t *dst;            // where its tokens go in the output (written by the gather, used by miss_copy_kernel)
     uint4 *skey;              // keys sorted by piece length (so that a warp merges pieces of one length)
     uint4 *smeta;             // {queue index, roff, pos, len} in the same order
     uint32_t cap;             // capacity of the queue (entries)
@@ -38,6 +39,7 @@ struct TileParams {
     const uint32_t *pbits; const uint32_t *dbits; const uint32_t *span_first_doc;
     const unsigned long long *doc_off; unsigned long long n_docs;
     LongQ q; const uint32_t *lidx; const uint32_t *ltok;
+    const uint32_t *doc_tiles;    // sub-tiles with a document start (sparse-document batches), count in ctr->n_doc_tiles
     const uint32_t *sbits;        // special-piece mask (NULL unless the call handles special tokens): id at ltok[start]
     uint32_t *ptok;               // [n_sub][SUB_BYTES] one slot per piece, in piece order
     MissQ mq; uint32_t *mres;     // miss queue and its token results
@@ -132,7 +134,7 @@ __global__ void __launch_bounds__(ENC_WARPS * 32) probe_kernel(TileParams p, Dev
         __syncwarp();
 
         // ---- whole-piece probe, two pieces per lane per iteration --------------------------------
-        uint32_t cnt = 0;                                      // tokens known so far (hits, single bytes, long pieces)
+        uint32_t cnt = 0;                                      // tokens known so far (hits, single bytes)
         auto prep = [&](uint32_t i, int &len, uint32_t &a0, uint32_t &a1, uint32_t &a2, uint32_t &a3) -> int {
             if (i >= np) return 0;
             const int off = S.plist[i];
@@ -141,18 +143,14 @@ __global__ void __launch_bounds__(ENC_WARPS * 32) probe_kernel(TileParams p, Dev
                 const long long pos = sub_byte + off;
                 if ((p.sbits[pos >> 5] >> (pos & 31)) & 1u) { st_stream_u32(slot + i, p.ltok[pos]); cnt++; return 0; }
             }
-            if (len > SHORT_MAX) {                             // long path: merged by the long-piece kernels before this one
-                const uint32_t qi = p.lidx[(sub_byte + off) >> 4];
-                cnt += p.q.ntok[qi];
+            if (len > SHORT_MAX) {                             // long path: merged by the long-piece kernels, concurrently, on a side
+                const uint32_t qi = p.lidx[(sub_byte + off) >> 4];     // stream (they credit their tokens to sub_count themselves)
                 st_stream_u32(slot + i, PT_LONG | qi);
                 return 0;
             }
-            if (len == 1) {
-                const uint32_t id = __ldg(T.byte_id + txt[off]);
-                if (id >= PSEUDO_BASE) { atomicOr(&p.ctr->err, ERR_NOBYTE); st_stream_u32(slot + i, PT_EMPTY); }
-                else { st_stream_u32(slot + i, id); cnt++; }
-                return 0;
-            }
+            // single-byte pieces (18 % of English) take the same path as the others: every single-byte token is in the
+            // piece table, and a byte the vocabulary lacks falls out as a miss whose merge reports ERR_NOBYTE -- one
+            // instruction stream for all lanes instead of a divergent branch
             load_key(txt, off, len, a0, a1, a2, a3);
             return 1;
         };
@@ -222,7 +220,7 @@ __global__ void __launch_bounds__(ENC_WARPS * 32) probe_kernel(TileParams p, Dev
             }
         }
         cnt = warp_sum_u32(cnt);
-        if (lane == 0) p.sub_count[sub] = cnt;                 // miss_kernel adds the tokens of the misses
+        if (lane == 0 && cnt) atomicAdd(p.sub_count + sub, cnt);   // the miss and long-piece kernels add theirs
         __syncwarp();                                          // everybody is done with buffer `cur` and the lists
     }
 }
@@ -231,6 +229,9 @@ __global__ void __launch_bounds__(ENC_WARPS * 32) probe_kernel(TileParams p, Dev
 // the misses, one piece per lane
 // --------------------------------------------------------------------------------------------
 static const int MISS_WARPS = 4;
+#ifndef MISS_MIN_BLOCKS
+#define MISS_MIN_BLOCKS 9
+#endif
 
 struct MissSmem {
     uint32_t id[SHORT_MAX * 32];       // [part][lane]
@@ -291,7 +292,7 @@ __global__ void __launch_bounds__(256) miss_scatter_kernel(TileParams p, const u
     }
 }
 
-__global__ void __launch_bounds__(MISS_WARPS * 32) miss_kernel(TileParams p, DevTables T) {
+__global__ void __launch_bounds__(MISS_WARPS * 32, MISS_MIN_BLOCKS) miss_kernel(TileParams p, DevTables T) {
     __shared__ MissSmem smem[MISS_WARPS];
     MissSmem &S = smem[threadIdx.x >> 5];
     const int lane = threadIdx.x & 31;
@@ -396,13 +397,20 @@ __global__ void add_offset_kernel(unsigned long long *a, unsigned long long n, l
 // --------------------------------------------------------------------------------------------
 static const int GATHER_WARPS = 8;
 
-// Two instantiations over the same grid: DOCS = false takes the sub-tiles without a document start (no shared memory,
-// 32 registers: full occupancy), DOCS = true the ones with (4 KiB of per-piece prefixes per warp); each skips the other's.
-template <bool DOCS>
-__global__ void __launch_bounds__(GATHER_WARPS * 32, DOCS ? 6 : 8) gather_kernel(TileParams p) {
+// MODE 0: every sub-tile, those with a document start skipped (no shared memory, 32 registers: full occupancy);
+// MODE 1: the sub-tiles of the doc-tile list (sparse documents: a few thousand of a million sub-tiles);
+// MODE 2: every sub-tile, all treated as holding document starts (dense documents: the list would be the whole grid).
+// MODE 1 / 2 keep 4 KiB of per-piece token prefixes per warp in shared memory.
+template <int MODE>
+__global__ void __launch_bounds__(GATHER_WARPS * 32, MODE ? 6 : 8) gather_kernel(TileParams p) {
+    constexpr bool DOCS = MODE != 0;
     __shared__ uint32_t s_pref[DOCS ? GATHER_WARPS : 1][DOCS ? SUB_BYTES + 1 : 1];
     const int lane = threadIdx.x & 31, warp = DOCS ? (threadIdx.x >> 5) : 0;
-    const long long sub = (long long)blockIdx.x * GATHER_WARPS + (threadIdx.x >> 5);
+    long long sub = (long long)blockIdx.x * GATHER_WARPS + (threadIdx.x >> 5);
+    if (MODE == 1) {
+        if (sub >= (long long)p.ctr->n_doc_tiles) return;
+        sub = (long long)p.doc_tiles[sub];
+    }
     if (sub >= p.n_sub) return;
     const unsigned long long base = p.sub_base[sub];
     const uint32_t *slot = p.ptok + sub * SUB_BYTES;
@@ -422,8 +430,7 @@ __global__ void __launch_bounds__(GATHER_WARPS * 32, DOCS ? 6 : 8) gather_kernel
     const uint32_t pinc = warp_incl_scan_u32(c, lane);
     const uint32_t pi0 = pinc - c;                           // index of this lane's first piece
     const uint32_t np = __shfl_sync(0xFFFFFFFFu, pinc, 31);
-    const bool has_docs = __any_sync(0xFFFFFFFFu, dm != 0);
-    if (has_docs != DOCS) return;
+    if (MODE == 0 && __any_sync(0xFFFFFFFFu, dm != 0)) return;           // a document starts here: MODE 1 takes this sub-tile
     uint32_t run = 0;                                        // tokens of the sub-tile so far
     // Software pipeline over steps of 32 pieces: the slot load of step t+2 and the count look-up of step t+1 (misses and
     // long pieces only) are in flight while step t is scanned and written, so a step does not wait for L2 twice.
@@ -447,10 +454,8 @@ __global__ void __launch_bounds__(GATHER_WARPS * 32, DOCS ? 6 : 8) gather_kernel
         unsigned long long lsrc = 0;
         if (n) {
             if (kind == 0) st_stream_u32(p.out + k, v);
-            else if (kind == PT_MISS) {
-                const uint32_t *src = p.mres + p.mq.roff[qi];
-                for (uint32_t x = 0; x < n; x++) st_stream_u32(p.out + k + x, src[x]);
-            } else {
+            else if (kind == PT_MISS) p.mq.dst[qi] = (uint32_t)k;     // copied by miss_copy_kernel, one miss per lane
+            else {
                 lsrc = p.q.start[qi];
                 if (n <= 32) for (uint32_t x = 0; x < n; x++) st_stream_u32(p.out + k + x, p.ltok[lsrc + x]);
             }
@@ -482,6 +487,17 @@ __global__ void __launch_bounds__(GATHER_WARPS * 32, DOCS ? 6 : 8) gather_kernel
                 while (d <= p.n_docs && p.doc_off[d] == pos) { p.tok_off[d] = tok; d++; }
             }
         }
+    }
+}
+
+// tokens of the missed pieces: mres -> their place in the output (found by the gather), one miss per lane
+__global__ void __launch_bounds__(256) miss_copy_kernel(TileParams p) {
+    const uint32_t n_miss = (p.ctr->err & ERR_MISSCAP) ? 0u : miss_count(p);
+    for (uint32_t qi = blockIdx.x * 256u + threadIdx.x; qi < n_miss; qi += gridDim.x * 256u) {
+        const uint32_t n = p.mq.cnt[qi];
+        const uint32_t *src = p.mres + p.mq.roff[qi];
+        uint32_t *dst = p.out + p.mq.dst[qi];
+        for (uint32_t x = 0; x < n; x++) st_stream_u32(dst + x, src[x]);
     }
 }
 

@@ -68,16 +68,16 @@ __global__ void __launch_bounds__(256) find_long_kernel(const uint32_t *__restri
             q.start[i] = (unsigned long long)s; q.len[i] = (unsigned int)len; q.off[i] = off; q.ntok[i] = 0;
             lidx[s >> 4] = i;
             // per-class work list, one atomic per (warp iteration, class)
-            const int c = !fits ? 7 : len > CLUSTER_MIN ? CLS_CLUSTER : len > BLOCK_MIN ? CLS_BLOCK : len > 256 ? CLS_WARP
-                          : len > 128 ? 3 : len > 64 ? 2 : len > 32 ? 1 : 0;
+            const int c = !fits ? N_CLS : len > CLUSTER_MIN ? CLS_CLUSTER : len > BLOCK_MIN ? CLS_BLOCK : len > GROUP_MAX ? CLS_WARP
+                          : len > 256 ? CLS_G1024 : len > 128 ? 3 : len > 64 ? 2 : len > 32 ? 1 : 0;
             const uint32_t same = __match_any_sync(peers, c);
             unsigned int k = 0;
             if ((threadIdx.x & 31) == __ffs(same) - 1) k = atomicAdd(&ctr->n_cls[c], (unsigned int)__popc(same));
             k = __shfl_sync(peers, k, __ffs(same) - 1) + __popc(same & ((1u << (threadIdx.x & 31)) - 1u));
-            if (c == 7) continue;
+            if (c == N_CLS) continue;
             // (constant indices: a dynamically indexed kernel parameter would be copied to local memory by every thread)
             unsigned int *lst = c == 0 ? q.cls[0] : c == 1 ? q.cls[1] : c == 2 ? q.cls[2] : c == 3 ? q.cls[3] : c == 4 ? q.cls[4]
-                                : c == 5 ? q.cls[5] : q.cls[6];
+                                : c == 5 ? q.cls[5] : c == 6 ? q.cls[6] : q.cls[7];
             lst[k] = i;
         }
     }
@@ -218,13 +218,13 @@ __device__ uint32_t long_piece_warp(const DevTables &T, const uint8_t *__restric
 static const int LONG_WARPS = 8;               // warps per block of long_piece_kernel
 
 __global__ void __launch_bounds__(LONG_WARPS * 32) long_piece_kernel(const uint8_t *__restrict__ text, DevTables T, LongQ q,
-                                                                    LongScratch S, uint32_t *ltok, Counters *ctr) {
+                                                                    LongScratch S, uint32_t *ltok, Counters *ctr, int cls) {
     const int lane = threadIdx.x & 31;
-    const unsigned int n_long = ctr->n_cls[CLS_WARP];
-    const unsigned int *list = q.cls[CLS_WARP];
+    const unsigned int n_long = ctr->n_cls[cls];
+    const unsigned int *list = cls == CLS_WARP ? q.cls[CLS_WARP] : q.cls[CLS_G1024];
     for (;;) {
         unsigned int k = 0;
-        if (lane == 0) k = atomicAdd(&ctr->cls_head[CLS_WARP], 1u);
+        if (lane == 0) k = atomicAdd(&ctr->cls_head[cls], 1u);
         k = __shfl_sync(0xFFFFFFFFu, k, 0);
         if (k >= n_long) break;
         const unsigned int i = list[k];
@@ -232,7 +232,7 @@ __global__ void __launch_bounds__(LONG_WARPS * 32) long_piece_kernel(const uint8
         LongScratch P = S;
         P.idA += off; P.rkA += off; P.idB += off; P.rkB += off; P.aux1 += off; P.aux2 += off; P.flag += off;
         const uint32_t nt = long_piece_warp(T, text + st0, q.len[i], P, ltok + st0, &ctr->err);
-        if (lane == 0) q.ntok[i] = nt;
+        if (lane == 0) long_piece_done(q, i, nt);
         __syncwarp();
     }
 }
@@ -398,7 +398,7 @@ __global__ void __launch_bounds__(GIANT_THREADS) giant_piece_kernel(const uint8_
         LongScratch P = S;
         P.idA += off; P.rkA += off; P.idB += off; P.rkB += off; P.aux1 += off; P.aux2 += off; P.flag += off;
         const uint32_t nt = long_piece_block(T, text + q.start[i], q.len[i], P, ltok + q.start[i], &ctr->err);
-        if (threadIdx.x == 0) q.ntok[i] = nt;
+        if (threadIdx.x == 0) long_piece_done(q, i, nt);
     }
 }
 
@@ -449,7 +449,7 @@ __device__ void mid_class(const uint8_t *__restrict__ text, const DevTables &T, 
                 h = long_hash_step(h, w, (uint32_t)(i >> 3));
             }
             const uint32_t r = piece_lookup_long(T, h, (uint32_t)n, [&](uint32_t i) { return piece[i]; });
-            if (r != RANK_MAX) { out[0] = r; q.ntok[qi] = 1; n = 0; }
+            if (r != RANK_MAX) { out[0] = r; long_piece_done(q, qi, 1); n = 0; }
         }
         n_max = (int)__reduce_max_sync(0xFFFFFFFFu, (unsigned)n);
         if (n_max) {
@@ -468,7 +468,7 @@ __device__ void mid_class(const uint8_t *__restrict__ text, const DevTables &T, 
                     if (x != ID_DEAD) { out[c++] = x; bad |= x >= PSEUDO_BASE; }
                 }
             }
-            if (n) q.ntok[qi] = c;
+            if (n) long_piece_done(q, qi, c);
             if (bad) atomicOr(&ctr->err, ERR_NOBYTE);
         }
         __syncwarp();
@@ -508,12 +508,15 @@ struct ClusterShared {
     uint32_t probe;           // whole-piece probe result (CTA 0)
 };
 
+// Every CTA owns a contiguous range of whole 1024-part tiles and every WARP a contiguous 1/32 of it (a multiple of 32
+// parts), which it walks 32 parts at a time with ballots and a carry in a register -- no block barrier inside a pass.
+// The carries (run parity of the selection, output offset of the compaction) enter a warp from its predecessors through
+// one exchange per pass: warp summaries in shared memory, CTA summaries in the peers' shared memory (DSMEM).
 __device__ uint32_t long_piece_cluster(cg::cluster_group &cluster, ClusterShared &sh, const DevTables &T,
                                        const uint8_t *__restrict__ piece, uint32_t n, LongScratch S,
                                        uint32_t *__restrict__ out, uint32_t *err) {
     __shared__ uint32_t s_red[32];
-    __shared__ uint32_t s_wmask[32];
-    __shared__ uint32_t s_carry;
+    __shared__ uint32_t s_wpar[32], s_wall[32], s_wcnt[32];      // per-warp summaries of the current pass
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const uint32_t rank = cluster.block_rank();
     const uint32_t gtid = rank * GIANT_THREADS + tid, gthreads = CLUSTER_CTAS * GIANT_THREADS;
@@ -541,11 +544,10 @@ __device__ uint32_t long_piece_cluster(cg::cluster_group &cluster, ClusterShared
     cluster.sync();
     uint32_t m = n;
     for (;;) {
-        // contiguous ranges of whole 1024-part tiles: a range that has a successor ends on a tile boundary (the tile loop
-        // below only carries the run parity across FULL tiles) and has an even length (a full range of candidates leaves
-        // the parity unchanged)
         const uint32_t chunk = (((m + CLUSTER_CTAS - 1) / CLUSTER_CTAS) + (GIANT_THREADS - 1)) & ~(uint32_t)(GIANT_THREADS - 1);
         const uint32_t lo = min(rank * chunk, m), hi = min(lo + chunk, m);
+        const uint32_t wchunk = chunk / 32;                              // a multiple of 32 parts per warp
+        const uint32_t wlo = min(lo + (uint32_t)wid * wchunk, hi), whi = min(wlo + wchunk, hi);
         // A. global minimum rank
         uint32_t g = RANK_MAX;
         for (uint32_t i = lo + tid; i < hi; i += GIANT_THREADS) g = min(g, rk[i]);
@@ -556,55 +558,40 @@ __device__ uint32_t long_piece_cluster(cg::cluster_group &cluster, ClusterShared
 #pragma unroll
         for (int c = 0; c < CLUSTER_CTAS; c++) g = min(g, *cluster.map_shared_rank(&sh.gmin, c));
         if (g == RANK_MAX) break;                        // the same value in every CTA
-        // B. select alternate members of every chain of consecutive candidates.  Pass `fin` = 0 only summarises the
-        //    range (parity of its trailing run, all candidates?), pass 1 selects with the carry-in of the predecessors.
-        for (int fin = 0; fin < 2; fin++) {
-            uint32_t carry_in = 0;
-            if (fin) {
-                for (int c = (int)rank - 1; c >= 0; c--) {
-                    if (*cluster.map_shared_rank(&sh.sel_all, c)) continue;      // a full range has an even length
-                    carry_in = *cluster.map_shared_rank(&sh.sel_par, c);
-                    break;
-                }
+        // B. select alternate members of every chain of consecutive candidates.
+        //    B1: every warp summarises its sub-range: parity of its trailing candidate run (carry-in 0), all candidates?
+        {
+            uint32_t par = 0; bool all = (whi - wlo) == wchunk;
+            for (uint32_t base = wlo; base < whi; base += 32) {
+                const uint32_t i = base + lane;
+                const uint32_t c = __ballot_sync(0xFFFFFFFFu, i < whi && rk[i] == g);
+                if (c != 0xFFFFFFFFu) { par = (uint32_t)__clz((int)~c) & 1u; all = false; }   // 32 more candidates: parity unchanged
             }
+            if (lane == 0) { s_wpar[wid] = par; s_wall[wid] = all ? 1u : 0u; }
             __syncthreads();
-            if (tid == 0) s_carry = carry_in;
-            __syncthreads();
-            bool noncand = false;
-            for (uint32_t base = lo; base < hi; base += GIANT_THREADS) {
-                const uint32_t i = base + tid;
-                const bool cand = i < hi && rk[i] == g;
-                noncand |= (i < hi) && !cand;
+            if (tid == 0) {
+                uint32_t cp = 0, ca = 1;
+                for (int w = 31; w >= 0; w--) { if (!s_wall[w]) { cp = s_wpar[w]; ca = 0; break; } }
+                sh.sel_par = cp; sh.sel_all = ca;
+            }
+            cluster.sync();
+        }
+        //    B2: carry-in = parity of the candidate run that ends right before the sub-range, then the selection itself
+        {
+            uint32_t carry = 0; bool found = false;
+            for (int w = wid - 1; w >= 0 && !found; w--) if (!s_wall[w]) { carry = s_wpar[w]; found = true; }   // full sub-ranges are even
+            for (int c = (int)rank - 1; c >= 0 && !found; c--)
+                if (!*cluster.map_shared_rank(&sh.sel_all, c)) { carry = *cluster.map_shared_rank(&sh.sel_par, c); found = true; }
+            for (uint32_t base = wlo; base < whi; base += 32) {
+                const uint32_t i = base + lane;
+                const bool cand = i < whi && rk[i] == g;
                 const uint32_t c = __ballot_sync(0xFFFFFFFFu, cand);
-                if (lane == 0) s_wmask[wid] = c;
-                __syncthreads();
-                uint32_t par = 0; bool open = true;
-                for (int w = wid - 1; w >= 0 && open; w--) {
-                    const uint32_t cw = s_wmask[w];
-                    if (cw == 0xFFFFFFFFu) continue;
-                    par = (uint32_t)__clz((int)~cw) & 1u; open = false;
-                }
-                if (open) par = s_carry;
                 const uint32_t zeros_below = ~c & ((1u << lane) - 1u);
                 uint32_t before;
-                if (zeros_below == 0) before = (uint32_t)lane + par;
+                if (zeros_below == 0) before = (uint32_t)lane + carry;
                 else before = (uint32_t)lane - (32u - (uint32_t)__clz((int)zeros_below));
-                if (fin && i < hi) S.flag[i] = (cand && ((before & 1u) == 0)) ? 1 : 0;
-                __syncthreads();
-                if (tid == GIANT_THREADS - 1) {
-                    uint32_t par2 = s_carry; bool open2 = true;
-                    for (int w = 31; w >= 0 && open2; w--) {
-                        const uint32_t cw = s_wmask[w];
-                        if (cw == 0xFFFFFFFFu) continue;
-                        par2 = (uint32_t)__clz((int)~cw) & 1u; open2 = false;
-                    }
-                    s_carry = par2;
-                }
-                __syncthreads();
-            }
-            if (!fin) {
-                const int any_non = __syncthreads_or(noncand ? 1 : 0);
-                if (tid == 0) { sh.sel_par = s_carry; sh.sel_all = (!any_non && hi - lo == chunk) ? 1u : 0u; }
+                if (i < whi) S.flag[i] = (cand && ((before & 1u) == 0)) ? 1 : 0;
+                if (c != 0xFFFFFFFFu) carry = (uint32_t)__clz((int)~c) & 1u;
             }
             cluster.sync();
         }
@@ -624,54 +611,54 @@ __device__ uint32_t long_piece_cluster(cg::cluster_group &cluster, ClusterShared
         uint32_t v = RANK_MAX;
 #pragma unroll
         for (int c = 0; c < CLUSTER_CTAS; c++) v = min(v, *cluster.map_shared_rank(&sh.vmin, c));
-        // D. commit merges at positions <= v, compact into the other buffer: count the range's survivors, exchange,
-        //    then write at the scanned offset
-        uint32_t surv = 0;
-        for (uint32_t base = lo; base < hi; base += GIANT_THREADS) {
-            const uint32_t i = base + tid;
-            const bool absorbed = i < hi && i >= 1 && S.flag[i - 1] && (i - 1) <= v;
-            surv += (uint32_t)__syncthreads_count(i < hi && !absorbed);
-        }
-        if (tid == 0) sh.n_surv = surv;
-        cluster.sync();
-        uint32_t prefix = 0, total = 0;
-#pragma unroll
-        for (int c = 0; c < CLUSTER_CTAS; c++) {
-            const uint32_t x = *cluster.map_shared_rank(&sh.n_surv, c);
-            if (c < (int)rank) prefix += x;
-            total += x;
-        }
-        __syncthreads();
-        if (tid == 0) s_carry = prefix;
-        __syncthreads();
-        for (uint32_t base = lo; base < hi; base += GIANT_THREADS) {
-            const uint32_t i = base + tid;
-            const bool in = i < hi;
-            const bool com = in && S.flag[i] && i <= v;
-            const bool absorbed = in && i >= 1 && S.flag[i - 1] && (i - 1) <= v;
-            const bool survive = in && !absorbed;
-            const uint32_t sb = __ballot_sync(0xFFFFFFFFu, survive);
-            if (lane == 0) s_wmask[wid] = (uint32_t)__popc(sb);
-            __syncthreads();
-            uint32_t wbase = s_carry;
-            for (int w = 0; w < wid; w++) wbase += s_wmask[w];
-            if (survive) {
-                uint32_t nid, nrk;
-                if (com) {
-                    nid = g;
-                    const bool com2 = (i + 2 < m) && S.flag[i + 2] && (i + 2) <= v;
-                    nrk = com2 ? S.aux1[i + 2] : S.aux2[i];
-                } else {
-                    nid = id[i];
-                    const bool com1 = (i + 1 < m) && S.flag[i + 1] && (i + 1) <= v;
-                    nrk = com1 ? S.aux1[i + 1] : rk[i];
-                }
-                const uint32_t o = wbase + __popc(sb & ((1u << lane) - 1u));
-                id2[o] = nid; rk2[o] = nrk;
+        // D. commit merges at positions <= v, compact into the other buffer.
+        //    D1: survivors per warp sub-range -> per CTA -> exchanged
+        {
+            uint32_t cnt = 0;
+            for (uint32_t base = wlo; base < whi; base += 32) {
+                const uint32_t i = base + lane;
+                const bool absorbed = i < whi && i >= 1 && S.flag[i - 1] && (i - 1) <= v;
+                cnt += (uint32_t)__popc(__ballot_sync(0xFFFFFFFFu, i < whi && !absorbed));
             }
+            if (lane == 0) s_wcnt[wid] = cnt;
             __syncthreads();
-            if (tid == 0) { uint32_t t = s_carry; for (int w = 0; w < 32; w++) t += s_wmask[w]; s_carry = t; }
-            __syncthreads();
+            if (tid == 0) { uint32_t t = 0; for (int w = 0; w < 32; w++) t += s_wcnt[w]; sh.n_surv = t; }
+            cluster.sync();
+        }
+        //    D2: every warp writes its survivors at its scanned offset
+        uint32_t total = 0;
+        {
+            uint32_t o = 0;
+#pragma unroll
+            for (int c = 0; c < CLUSTER_CTAS; c++) {
+                const uint32_t x = *cluster.map_shared_rank(&sh.n_surv, c);
+                if (c < (int)rank) o += x;
+                total += x;
+            }
+            for (int w = 0; w < wid; w++) o += s_wcnt[w];
+            for (uint32_t base = wlo; base < whi; base += 32) {
+                const uint32_t i = base + lane;
+                const bool in = i < whi;
+                const bool com = in && S.flag[i] && i <= v;
+                const bool absorbed = in && i >= 1 && S.flag[i - 1] && (i - 1) <= v;
+                const bool survive = in && !absorbed;
+                const uint32_t sb = __ballot_sync(0xFFFFFFFFu, survive);
+                if (survive) {
+                    uint32_t nid, nrk;
+                    if (com) {
+                        nid = g;
+                        const bool com2 = (i + 2 < m) && S.flag[i + 2] && (i + 2) <= v;
+                        nrk = com2 ? S.aux1[i + 2] : S.aux2[i];
+                    } else {
+                        nid = id[i];
+                        const bool com1 = (i + 1 < m) && S.flag[i + 1] && (i + 1) <= v;
+                        nrk = com1 ? S.aux1[i + 1] : rk[i];
+                    }
+                    const uint32_t oo = o + __popc(sb & ((1u << lane) - 1u));
+                    id2[oo] = nid; rk2[oo] = nrk;
+                }
+                o += (uint32_t)__popc(sb);
+            }
         }
         cluster.sync();                                  // the compacted arrays are complete and visible
         m = total;
@@ -705,7 +692,7 @@ __global__ void __cluster_dims__(CLUSTER_CTAS, 1, 1) __launch_bounds__(GIANT_THR
         LongScratch P = S;
         P.idA += off; P.rkA += off; P.idB += off; P.rkB += off; P.aux1 += off; P.aux2 += off; P.flag += off;
         const uint32_t nt = long_piece_cluster(cluster, sh, T, text + q.start[i], q.len[i], P, ltok + q.start[i], &ctr->err);
-        if (rank == 0 && threadIdx.x == 0) q.ntok[i] = nt;
+        if (rank == 0 && threadIdx.x == 0) long_piece_done(q, i, nt);
         cluster.sync();
     }
 }
