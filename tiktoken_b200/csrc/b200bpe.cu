@@ -335,6 +335,7 @@ static int devctx_create(b200bpe *h, int device, const std::vector<uint32_t> &bo
     D->uc.ascii = D->arena + parts[4].off;
     D->uc.stage1 = (const uint16_t *)(D->arena + parts[5].off);
     D->uc.stage2 = D->arena + parts[6].off;
+    D->uc.one = 1u;
     D->T.long_tab = (const U4 *)(D->arena + parts[7].off); D->T.long_mask = H.long_mask;
     D->T.long_blob = D->arena + parts[8].off;
     D->T.max_token_len = H.max_token_len; D->T.n_long_tokens = H.n_long_tokens;

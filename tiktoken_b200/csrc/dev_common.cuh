@@ -17,7 +17,10 @@ static const uint32_t ERR_MISSCAP = 16u;    // miss queue / miss result space to
 static const uint32_t ERR_SLOWCAP = 64u;    // list of positions for the general rule function too small               -> host grows it and re-runs
 static const uint32_t ERR_SPECIAL = 32u;    // a disallowed special token occurs in the text (tiktoken/core.py:120-124)
 
-struct UcTables { const uint16_t *stage1; const uint8_t *stage2; const uint8_t *ascii; };
+struct UcTables {
+    const uint16_t *stage1; const uint8_t *stage2; const uint8_t *ascii;
+    uint32_t one;            // == 1, opaque to the compiler: keeps v * one + c an IMAD (FMA pipe) in the pre-tokeniser's byte tests
+};
 
 static const int N_CLS = 8;                  // length classes of pieces longer than SHORT_MAX (see LongQ::cls)
 static const int CLS_G1024 = 4, CLS_WARP = 5, CLS_BLOCK = 6, CLS_CLUSTER = 7;

@@ -62,7 +62,7 @@ __global__ void __launch_bounds__(PRETOK_WARPS * 32, PAT == PAT_O200K ? 4 : 5) p
     __shared__ uint32_t s_cnt, s_base;
     const long long w = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31;
-    const TextAccess t{text, n_bytes, dbits, uc.stage1, uc.stage2, uc.ascii};
+    const TextAccess t{text, n_bytes, dbits, uc.stage1, uc.stage2, uc.ascii, uc.one};
     if (threadIdx.x == 0) s_cnt = 0;
     uint64_t b = 0, slow = 0;
     if (w < n_words) b = span_fast<PAT>(t, w, slow);

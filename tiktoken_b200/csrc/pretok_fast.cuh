@@ -25,11 +25,82 @@ struct SpanStats { unsigned long long positions, slow; };
 #define B2_POPCLL(x) __builtin_popcountll(x)
 #endif
 
-B2_HD uint32_t swar_ge(uint32_t y7, uint32_t n) {          // per byte: y7 (7-bit) >= n  -> 0x80 flag
-    return (y7 + (0x80u - n) * 0x01010101u) & 0x80808080u;
+// ---- SWAR classification of the 48-byte window ------------------------------------------------------------------
+// The window's bytes are first TRANSPOSED with byte permutes (PRMT): own word T[k] holds the own bytes {k, 8+k, 16+k,
+// 24+k}, halo word H[k] the halo bytes {k, 4+k | 40+k, 44+k}.  A per-byte test leaves its answer in bit 7 of every byte
+// (other bits: don't care, all combining logic is bitwise); with the transposed layout the 32 answers of a class fall
+// into place with ONE shift-and-or per word -- acc |= f >> (7-k) puts byte 8j+k at bit 8j+k -- instead of a
+// multiply-gather and a 64-bit insert per word and class.
+B2_HD uint32_t b2_prmt(uint32_t a, uint32_t b, uint32_t sel) {
+#if defined(__CUDA_ARCH__)
+    return __byte_perm(a, b, sel);
+#else
+    const uint64_t v = ((uint64_t)b << 32) | a;
+    uint32_t r = 0;
+    for (int i = 0; i < 4; i++) r |= (uint32_t)((v >> (8 * ((sel >> (4 * i)) & 7u))) & 0xFFu) << (8 * i);
+    return r;
+#endif
 }
-B2_HD uint32_t swar_gather(uint32_t flags80) {             // four 0x80 flags -> 4-bit nibble
-    return (((flags80 >> 7) * 0x00204081u) >> 21) & 0xFu;
+// 4 x 4 byte transpose: t[k] = { a.byte k, b.byte k, c.byte k, d.byte k }
+B2_HD void transpose4(uint32_t a, uint32_t b, uint32_t c, uint32_t d, uint32_t &t0, uint32_t &t1, uint32_t &t2, uint32_t &t3) {
+    const uint32_t ab_lo = b2_prmt(a, b, 0x5140u), ab_hi = b2_prmt(a, b, 0x7362u);
+    const uint32_t cd_lo = b2_prmt(c, d, 0x5140u), cd_hi = b2_prmt(c, d, 0x7362u);
+    t0 = b2_prmt(ab_lo, cd_lo, 0x5410u); t1 = b2_prmt(ab_lo, cd_lo, 0x7632u);
+    t2 = b2_prmt(ab_hi, cd_hi, 0x5410u); t3 = b2_prmt(ab_hi, cd_hi, 0x7632u);
+}
+
+struct ClassAcc {             // bit (8j + k) of every member = the answer for byte lane j of transposed word k
+    uint32_t hi, cont, al, up, dg, sp, ws, nl, ap, sl;
+};
+B2_HD uint32_t b2_mad1(uint32_t v, uint32_t one, uint32_t c) {   // v * one + c as ONE multiply-add (no common `v * one`)
+#if defined(__CUDA_ARCH__)
+    uint32_t r;
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(v), "r"(one), "r"(c));
+    return r;
+#else
+    return v * one + c;
+#endif
+}
+// The byte tests of one (transposed) word.  Pipe balance matters more than the instruction count here: ncu shows the
+// kernel bound by the ALU pipe (LOP3 / SHF / IADD3: one warp instruction per two cycles and scheduler; 94 % busy in round 1)
+// while the FMA pipe, which executes IMAD, idles.  So the 15 per-byte comparisons of a word are written as multiply-adds
+// (v * one + c with `one` == 1 at run time, opaque to the compiler -> IMAD); the combining logic and the accumulation
+// (one LEA.HI / SHF+LOP3 per class) stay on the ALU pipe.  A multiply-high accumulate (IMAD.HI) was measured too: it
+// moves more work off the ALU pipe but IMAD.HI issues at a quarter of the IMAD rate (profiles/r02_f_pretok_pipes.txt).
+#ifndef B2_CLASSIFY_FMA
+#define B2_CLASSIFY_FMA 1
+#endif
+template <int K>
+B2_HD void classify_word(uint32_t x, ClassAcc &a, uint32_t one) {
+    const uint32_t y = x & 0x7F7F7F7Fu, yl = y | 0x20202020u;
+    const uint32_t hi7 = x & 0x80808080u, nx7 = hi7 ^ 0x80808080u;       // bit 7 of every byte: non-ASCII / ASCII
+#if B2_CLASSIFY_FMA
+#define B2_GE(v, n) b2_mad1(v, one, (0x80u - (uint32_t)(n)) * 0x01010101u)  /* bit 7 of every byte: (7-bit v) >= n */
+#else
+#define B2_GE(v, n) ((v) + (0x80u - (uint32_t)(n)) * 0x01010101u)
+#endif
+    const uint32_t alpha = B2_GE(yl, 'a') & ~B2_GE(yl, 'z' + 1) & nx7;
+    const uint32_t upper = alpha & ~(x << 2);                              // bit 5 clear
+    const uint32_t digit = B2_GE(y, '0') & ~B2_GE(y, '9' + 1) & nx7;
+    const uint32_t space = B2_GE(y, 0x20) & ~B2_GE(y, 0x21) & nx7;
+    const uint32_t g0e = B2_GE(y, 0x0E);
+    const uint32_t nl_a = B2_GE(y, 0x0A) & ~B2_GE(y, 0x0B) & nx7, nl_d = B2_GE(y, 0x0D) & ~g0e & nx7;
+    const uint32_t ws5 = B2_GE(y, 0x09) & ~g0e & nx7;                      // 0x09..0x0D; CR / LF are taken out on the masks
+    const uint32_t apos = B2_GE(y, 0x27) & ~B2_GE(y, 0x28) & nx7;
+    const uint32_t slash = B2_GE(y, 0x2F) & ~B2_GE(y, 0x30) & nx7;
+    const uint32_t cnt = hi7 & ~(x << 1);                                  // 10xxxxxx
+#undef B2_GE
+#define B2_ACC(dst, f) dst |= (f) >> (7 - K)                               /* the answers are masked to bit 7 of every byte */
+    B2_ACC(a.hi, hi7); B2_ACC(a.cont, cnt); B2_ACC(a.al, alpha); B2_ACC(a.up, upper); B2_ACC(a.dg, digit);
+    B2_ACC(a.sp, space); B2_ACC(a.ws, ws5); B2_ACC(a.nl, nl_a); B2_ACC(a.nl, nl_d); B2_ACC(a.ap, apos); B2_ACC(a.sl, slash);
+#undef B2_ACC
+}
+
+// own answers (bit i = own byte i) and halo answers (nibbles at bits 0, 8 | 16, 24) -> window mask (bit i = window byte i)
+B2_HD uint64_t window_mask(uint32_t own, uint32_t halo) {
+    const uint32_t pre = (halo & 0xFu) | ((halo >> 4) & 0xF0u);
+    const uint32_t post = ((halo >> 16) & 0xFu) | ((halo >> 20) & 0xF0u);
+    return (uint64_t)pre | ((uint64_t)own << 8) | ((uint64_t)post << 40);
 }
 
 struct WinMasks {
@@ -61,33 +132,19 @@ B2_HD void classify_window(const TextAccess &t, int64_t win0, int64_t w, WinMask
     uint64_t valid = 0xFFFFFFFFFFFFull;
     if (win0 < 0) valid &= ~((1ull << (-win0)) - 1ull);
     if (win0 + 48 > n) { int64_t keep = n - win0; valid &= keep <= 0 ? 0ull : ((1ull << keep) - 1ull); }
-    uint64_t hi = 0, cont = 0, al = 0, up = 0, dg = 0, sp = 0, ws = 0, nl = 0, ap = 0, sl = 0;
-#if defined(__CUDA_ARCH__)
-#pragma unroll
-#endif
-    for (int k = 0; k < 12; k++) {
-        const uint32_t x = W[k];
-        const uint32_t h = x & 0x80808080u, y = x & 0x7F7F7F7Fu, yl = y | 0x20202020u;
-        const uint32_t nh = ~h;
-        const uint32_t alpha = swar_ge(yl, 'a') & ~swar_ge(yl, 'z' + 1) & nh;
-        const uint32_t upper = alpha & ~((x & 0x20202020u) << 2);
-        const uint32_t digit = swar_ge(y, '0') & ~swar_ge(y, '9' + 1) & nh;
-        const uint32_t g20 = swar_ge(y, 0x20), g21 = swar_ge(y, 0x21);
-        const uint32_t space = g20 & ~g21 & nh;
-        const uint32_t g09 = swar_ge(y, 0x09), g0a = swar_ge(y, 0x0A), g0b = swar_ge(y, 0x0B);
-        const uint32_t g0d = swar_ge(y, 0x0D), g0e = swar_ge(y, 0x0E);
-        const uint32_t newl = ((g0a & ~g0b) | (g0d & ~g0e)) & nh;
-        const uint32_t wsp = g09 & ~g0e & nh & ~newl;
-        const uint32_t apos = swar_ge(y, 0x27) & ~swar_ge(y, 0x28) & nh;
-        const uint32_t slash = swar_ge(y, 0x2F) & ~swar_ge(y, 0x30) & nh;
-        const uint32_t cnt = h & ~((x & 0x40404040u) << 1);
-        const int s = 4 * k;
-        hi |= (uint64_t)swar_gather(h) << s;       cont |= (uint64_t)swar_gather(cnt) << s;
-        al |= (uint64_t)swar_gather(alpha) << s;   up |= (uint64_t)swar_gather(upper) << s;
-        dg |= (uint64_t)swar_gather(digit) << s;   sp |= (uint64_t)swar_gather(space) << s;
-        ws |= (uint64_t)swar_gather(wsp) << s;     nl |= (uint64_t)swar_gather(newl) << s;
-        ap |= (uint64_t)swar_gather(apos) << s;    sl |= (uint64_t)swar_gather(slash) << s;
-    }
+    uint32_t T[8], H[4];
+    transpose4(W[2], W[4], W[6], W[8], T[0], T[1], T[2], T[3]);          // own bytes 8j + k      (k = 0..3)
+    transpose4(W[3], W[5], W[7], W[9], T[4], T[5], T[6], T[7]);          //                        (k = 4..7)
+    transpose4(W[0], W[1], W[10], W[11], H[0], H[1], H[2], H[3]);        // halo: window bytes k, 4+k | 40+k, 44+k
+    ClassAcc o = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, h = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    const uint32_t one = t.one;
+    classify_word<0>(T[0], o, one); classify_word<1>(T[1], o, one); classify_word<2>(T[2], o, one); classify_word<3>(T[3], o, one);
+    classify_word<4>(T[4], o, one); classify_word<5>(T[5], o, one); classify_word<6>(T[6], o, one); classify_word<7>(T[7], o, one);
+    classify_word<0>(H[0], h, one); classify_word<1>(H[1], h, one); classify_word<2>(H[2], h, one); classify_word<3>(H[3], h, one);
+    const uint64_t hi = window_mask(o.hi, h.hi), cont = window_mask(o.cont, h.cont), al = window_mask(o.al, h.al);
+    const uint64_t up = window_mask(o.up, h.up), dg = window_mask(o.dg, h.dg), sp = window_mask(o.sp, h.sp);
+    const uint64_t nl = window_mask(o.nl, h.nl), ws = window_mask(o.ws, h.ws) & ~nl, ap = window_mask(o.ap, h.ap);
+    const uint64_t sl = window_mask(o.sl, h.sl);
     m.valid = valid; m.hi = hi & valid; m.cont = cont & valid;
     m.LU = up & valid; m.LL = (al & ~up) & valid; m.LB = 0; m.M = 0;
     m.N = dg & valid; m.NA = m.N; m.SP = sp & valid; m.WS = ws & valid; m.NL = nl & valid;

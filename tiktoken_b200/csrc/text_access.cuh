@@ -14,6 +14,7 @@ struct TextAccess {
     const uint16_t *stage1;         // Unicode class table, 256-code-point blocks
     const uint8_t *stage2;
     const uint8_t *ascii;           // 128 class bytes for U+0000..U+007F
+    uint32_t one = 1u;              // the constant 1, opaque to the device compiler (see classify_word)
 
     B2_HD unsigned byte(int64_t pos) const { return text[pos]; }
     B2_HD bool doc_start(int64_t pos) const { return (dbits[pos >> 5] >> (pos & 31)) & 1u; }
