@@ -14,7 +14,7 @@ import subprocess
 
 _CSRC = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc")
 _SO = os.path.join(_CSRC, "libb200bpe.so")
-_SOURCES = ["b200bpe.cu", "dev_common.cuh", "kernels_pretok.cuh", "kernels_long.cuh", "kernels_mid.cuh", "kernels_encode.cuh",
+_SOURCES = ["b200bpe.cu", "dev_common.cuh", "kernels_pretok.cuh", "kernels_long.cuh", "kernels_mid.cuh", "kernels_pmerge.cuh", "kernels_encode.cuh",
             "kernels_special.cuh", "kernels_decode.cuh", "bpe_device.cuh", "bpe_tables.h", "pretok_rules.cuh",
             "pretok_fast.cuh", "text_access.cuh", "unicode_classes.inc"]
 

@@ -46,6 +46,7 @@
 #include "kernels_pretok.cuh"
 #include "kernels_long.cuh"
 #include "kernels_mid.cuh"
+#include "kernels_pmerge.cuh"
 #include "kernels_encode.cuh"
 #include "kernels_special.cuh"
 #include "kernels_decode.cuh"
@@ -231,6 +232,8 @@ struct b200bpe {
     size_t chunk_bytes = 64u << 20; bool chunk_forced = false;
     int copy_threads = 4;
     bool mid_group = true;           // 17..1024-byte pieces: group-of-lanes kernels (need ranks < 2^22)
+    bool pmerge = true;              // 129..1024-byte pieces: segmented parallel merge (needs ranks < 2^22); off: the group-of-lanes kernels
+    int pmerge_min_cls = 3;          // shortest length class the parallel merge takes (3: 129..256 bytes; 0: everything from 17 bytes)
     std::mutex mu;
     std::vector<PinnedBuf> pinned_pool;
     // results keep the engine alive: b200bpe_destroy with results outstanding only marks the handle dead, the last
@@ -420,6 +423,8 @@ extern "C" int b200bpe_create_multi(const uint8_t *tok_bytes, const uint64_t *to
     }
     if (const char *cm = getenv("B200BPE_CHUNK_MB")) { long v = atol(cm); if (v >= 1 && v <= 2048) { h->chunk_bytes = (size_t)v << 20; h->chunk_forced = true; } }
     h->mid_group = H.max_rank < MIDG_MAX_RANK && env_long("B200BPE_MID_GROUP", 1, 0, 1) != 0;
+    h->pmerge = h->mid_group && env_long("B200BPE_PMERGE", 1, 0, 1) != 0;
+    h->pmerge_min_cls = (int)env_long("B200BPE_PMERGE_MIN_CLS", 3, 0, 3);
     h->copy_threads = (int)env_long("B200BPE_COPY_THREADS", std::max(1u, std::min(8u, std::thread::hardware_concurrency() / 4)), 1, 64);
     h->table_bytes[0] = H.piece_tab.size() * sizeof(U4);
     h->table_bytes[1] = H.pair_tab.size() * sizeof(U4) + 65536 * 4 + 1024;
@@ -617,8 +622,13 @@ static int enqueue_pipeline(b200bpe *h, DevCtx *D, Slot &S, const PipeArgs &a) {
         CUDA_TRY(cudaStreamWaitEvent(ls2, S.ev[10], 0));
         CUDA_TRY(cudaEventRecord(S.ev[11], ls));
         LongScratch LS{S.w_idA.p, S.w_rkA.p, S.w_idB.p, S.w_rkB.p, S.w_aux1.p, S.w_aux2.p, S.w_flag.p};
-        if (h->mid_group) {      // 17..1024 bytes: a group of lanes per piece, state in shared memory
-            mid_group32_kernel<<<148 * 4, MIDG_WARPS * 32, 0, ls>>>(a.d_text, D->T, q, S.w_ltok.p, S.d_ctr);
+        if (h->pmerge) {         // 129..1024 bytes: segmented parallel merge (rounds, not merges, are sequential); shorter: a group of lanes per piece
+            pmerge_kernel<<<148 * 5, PM_WARPS * 32, 0, ls>>>(a.d_text, D->T, q, S.w_ltok.p, S.d_ctr, h->pmerge_min_cls);
+            pmerge_long_kernel<<<148 * 4, PM_WARPS_L * 32, 0, ls>>>(a.d_text, D->T, q, S.w_ltok.p, S.d_ctr);
+            if (h->pmerge_min_cls > 2) mid_group32_kernel<<<148 * 4, MIDG_WARPS * 32, 0, ls>>>(a.d_text, D->T, q, S.w_ltok.p, S.d_ctr, 2);
+            if (h->pmerge_min_cls > 0) mid_group16_kernel<<<148 * 9, MIDG_WARPS * 32, 0, ls>>>(a.d_text, D->T, q, S.w_ltok.p, S.d_ctr);
+        } else if (h->mid_group) {      // 17..1024 bytes: a group of lanes per piece, state in shared memory
+            mid_group32_kernel<<<148 * 4, MIDG_WARPS * 32, 0, ls>>>(a.d_text, D->T, q, S.w_ltok.p, S.d_ctr, 4);
             mid_group16_kernel<<<148 * 9, MIDG_WARPS * 32, 0, ls>>>(a.d_text, D->T, q, S.w_ltok.p, S.d_ctr);
         } else {                 // ranks of 2^22 and above: one piece per lane (72 KiB of columns per block) / warp per piece
             mid_thread_kernel<<<148 * 3, MID_WARPS * 32, MID_SMEM_BYTES, ls>>>(a.d_text, D->T, q, S.w_ltok.p, S.d_ctr);
@@ -712,6 +722,7 @@ static int collect_pipeline(b200bpe *h, Slot &S, int *special_idx, uint64_t *spe
         }
         return B200BPE_RETRY;
     }
+    if (c.err & ERR_INTERNAL) return fail(B200BPE_ECUDA, "internal error: a merge kernel did not converge");
     if (c.err & ERR_NOBYTE)
         return fail(B200BPE_ENOBYTE, "a piece needs a single-byte token that mergeable_ranks does not contain");
     return B200BPE_OK;

@@ -15,6 +15,7 @@ static const uint32_t ERR_BADTOKEN = 4u;    // decode: unknown token id
 static const uint32_t ERR_LONGCAP = 8u;     // long-piece merge scratch too small for this batch  -> host grows it and re-runs
 static const uint32_t ERR_MISSCAP = 16u;    // miss queue / miss result space too small            -> host grows it and re-runs
 static const uint32_t ERR_SLOWCAP = 64u;    // list of positions for the general rule function too small               -> host grows it and re-runs
+static const uint32_t ERR_INTERNAL = 128u;  // a kernel invariant did not hold (reported, never silently wrong)
 static const uint32_t ERR_SPECIAL = 32u;    // a disallowed special token occurs in the text (tiktoken/core.py:120-124)
 
 struct UcTables {

@@ -228,11 +228,11 @@ __device__ void midg_class(const uint8_t *__restrict__ text, const DevTables &T,
 
 // 32 parts per lane (12 KiB of state per warp): 257..1024, 129..256 and 65..128 bytes
 __global__ void __launch_bounds__(MIDG_WARPS * 32, 4) mid_group32_kernel(const uint8_t *__restrict__ text, DevTables T, LongQ q,
-                                                                        uint32_t *ltok, Counters *ctr) {
+                                                                        uint32_t *ltok, Counters *ctr, int max_cls) {
     __shared__ MidGSmem<32> smem[MIDG_WARPS];
     MidGSmem<32> &S = smem[threadIdx.x >> 5];
-    midg_class<32, 32>(text, T, q, 4, ltok, ctr, S);
-    midg_class<8, 32>(text, T, q, 3, ltok, ctr, S);
+    if (max_cls >= 4) midg_class<32, 32>(text, T, q, 4, ltok, ctr, S);
+    if (max_cls >= 3) midg_class<8, 32>(text, T, q, 3, ltok, ctr, S);
     midg_class<4, 32>(text, T, q, 2, ltok, ctr, S);
 }
 
