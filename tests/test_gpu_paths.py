@@ -28,19 +28,21 @@ def _oracle(ranks, special, pat):
     return Oracle(ranks, special, pat)
 
 
-def _chunked_encoding(enc_name, chunk_mb):
-    """An Encoding whose host pipeline cuts batches into chunk_mb-MiB chunks (read at construction)."""
+def _chunked_encoding(enc_name, chunk_mb, **env):
+    """An Encoding whose host pipeline cuts batches into chunk_mb-MiB chunks (knobs are read at construction)."""
     import tiktoken_b200
     pat, ranks, special, _ = vu.load_encoding(enc_name, allow_real=False)
-    old = os.environ.get("B200BPE_CHUNK_MB")
-    os.environ["B200BPE_CHUNK_MB"] = str(chunk_mb)
+    env = dict(env, B200BPE_CHUNK_MB=chunk_mb)
+    old = {k: os.environ.get(k) for k in env}
+    os.environ.update({k: str(v) for k, v in env.items()})
     try:
         e = tiktoken_b200.Encoding(enc_name + "_chunk", pat_str=pat, mergeable_ranks=ranks, special_tokens=special)
     finally:
-        if old is None:
-            os.environ.pop("B200BPE_CHUNK_MB", None)
-        else:
-            os.environ["B200BPE_CHUNK_MB"] = old
+        for k, v in old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
     return e, _oracle(ranks, special, pat), special
 
 
@@ -83,6 +85,21 @@ def test_chunk_seams_1mib_chunks(enc, kind):
         docs.append("".join(parts) + s[prev:])
     got = e.encode_batch(docs, allowed_special="all")
     assert got == [o.encode(d, set(special)) for d in docs]
+
+
+@pytest.mark.parametrize("enc,kind", [("cl100k_base", corpus.ENGLISH), ("o200k_base", corpus.MIXED), ("r50k_base", corpus.CODE)])
+def test_bit_packed_token_return(enc, kind):
+    """B200BPE_PACK=1: tokens cross PCIe as 16..18-bit fields (pack_tokens_kernel) and helper threads widen them into the
+    result next to the pipeline -- many small chunks, pinned and pageable input, every token compared."""
+    e, o, _ = _chunked_encoding(enc, 1, B200BPE_PACK=1, B200BPE_COPY_THREADS=5)
+    text = corpus.generate(kind, 77, 9 << 20)
+    off = corpus.docs_fixed(text, 50_000, at_space=True)[1]
+    exp_t, exp_o = o.encode_ordinary_batch_np(text, off, CORES)
+    assert _same(e.encode_ordinary_packed(text, off), exp_t, exp_o)
+    assert _same(e.encode_ordinary_packed(text.copy(), off), exp_t, exp_o)
+    one = np.asarray([0, len(text)], np.uint64)                  # one document: one pipeline pass, one packed block
+    exp_t, exp_o = o.encode_ordinary_batch_np(text, one, CORES)
+    assert _same(e.encode_ordinary_packed(text, one), exp_t, exp_o)
 
 
 def test_default_chunks_over_200mib_full_compare():

@@ -36,6 +36,9 @@
 
 #include <algorithm>
 #include <atomic>
+#include <condition_variable>
+#include <deque>
+#include <functional>
 #include <mutex>
 #include <string>
 #include <thread>
@@ -110,17 +113,54 @@ long env_long(const char *name, long dflt, long lo, long hi) {
     return x < lo ? lo : x > hi ? hi : x;
 }
 
-void parallel_memcpy(void *dst, const void *src, size_t n, int threads) {
-    if (threads <= 1 || n < (8u << 20)) { memcpy(dst, src, n); return; }
-    std::vector<std::thread> th;
-    const size_t part = ((n + threads - 1) / threads + 4095) & ~(size_t)4095;
-    for (int t = 0; t < threads; t++) {
-        const size_t lo = (size_t)t * part;
-        if (lo >= n) break;
-        const size_t len = std::min(part, n - lo);
-        th.emplace_back([=] { memcpy((uint8_t *)dst + lo, (const uint8_t *)src + lo, len); });
+// Persistent helper threads of one engine: they widen the bit-packed tokens that come back over PCIe and stage pageable
+// caller memory into pinned blocks, next to the device pipeline (the reference's counterpart is its rayon / thread pool).
+struct TaskPool {
+    std::vector<std::thread> th; std::mutex mu; std::condition_variable cv; std::deque<std::function<void()>> q; bool stop = false;
+    void ensure(int n) {
+        std::lock_guard<std::mutex> lk(mu);
+        while ((int)th.size() < n) th.emplace_back([this] {
+            for (;;) {
+                std::function<void()> f;
+                {
+                    std::unique_lock<std::mutex> lk(mu);
+                    cv.wait(lk, [this] { return stop || !q.empty(); });
+                    if (q.empty()) return;
+                    f = std::move(q.front()); q.pop_front();
+                }
+                f();
+            }
+        });
     }
-    for (auto &t : th) t.join();
+    void push(std::function<void()> f) { { std::lock_guard<std::mutex> lk(mu); q.push_back(std::move(f)); } cv.notify_one(); }
+    ~TaskPool() {
+        { std::lock_guard<std::mutex> lk(mu); stop = true; }
+        cv.notify_all();
+        for (auto &t : th) t.join();
+    }
+};
+struct Latch {
+    std::mutex mu; std::condition_variable cv; int left;
+    explicit Latch(int n) : left(n) {}
+    void done() { std::lock_guard<std::mutex> lk(mu); if (--left == 0) cv.notify_all(); }
+    void wait() { std::unique_lock<std::mutex> lk(mu); cv.wait(lk, [this] { return left == 0; }); }
+};
+// fn(lo, hi) over [0, n) in blocks, on the pool; the caller waits
+void pool_for(TaskPool *pool, size_t n, size_t block, const std::function<void(size_t, size_t)> &fn) {
+    const size_t nb = (n + block - 1) / block;
+    if (!pool || nb <= 1) { if (n) fn(0, n); return; }
+    Latch latch((int)nb);
+    for (size_t b = 0; b < nb; b++) pool->push([&, b] { fn(b * block, std::min(n, (b + 1) * block)); latch.done(); });
+    latch.wait();
+}
+// tokens come back from the device as `bits`-bit fields, little-endian bit order (pack_tokens_kernel); src is readable 8 bytes past the end
+void unpack_tokens(const uint8_t *src, uint32_t *dst, size_t lo, size_t hi, int bits) {
+    const uint64_t mask = (1ull << bits) - 1ull;
+    size_t bitpos = lo * (size_t)bits;
+    for (size_t i = lo; i < hi; i++, bitpos += (size_t)bits) {
+        uint64_t x; memcpy(&x, src + (bitpos >> 3), 8);
+        dst[i] = (uint32_t)((x >> (bitpos & 7)) & mask);
+    }
 }
 
 }  // namespace
@@ -143,9 +183,13 @@ struct Slot {
     cudaStream_t stream = nullptr;
     cudaStream_t side = nullptr;     // the group kernels (17..1024 bytes) run here, next to probe + miss on the main stream,
     cudaStream_t side2 = nullptr;    // and the scratch kernels (warp / block / cluster per piece: a few SMs each) here
-    static const int N_EV = 14;       // [10] fork, [11] side start, [12] side end (join), [13] side2 end (join)
+    cudaStream_t up = nullptr;       // host path: uploads of the slot's NEXT chunk (ordered behind the kernels, not the download, of its last one)
+    static const int N_EV = 15;       // [10] fork, [11] side start, [12] side end (join), [13] side2 end (join), [14] packed tokens on the host
     cudaEvent_t ev[N_EV];
     PinnedBuf stage;                // pinned staging for callers whose text is pageable memory
+    DevBuf<uint32_t> w_pack;        // bit-packed tokens of the chunk (host path)
+    PinnedBuf stage_out;            // ... and where they land on the host before the helper threads widen them
+    std::atomic<int> stage_out_busy{0};
     float last_ms[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
     uint32_t last_launches = 0;
     bool ok = false;
@@ -158,6 +202,7 @@ struct Slot {
         if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking);
         if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking);
         if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&side2, cudaStreamNonBlocking);
+        if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&up, cudaStreamNonBlocking);
         for (int i = 0; i < N_EV && e == cudaSuccess; i++) e = cudaEventCreate(&ev[i]);
         ok = (e == cudaSuccess);
         return e;
@@ -171,9 +216,11 @@ struct Slot {
         w_lq_start.release(); w_lq_off.release(); w_lq_len.release(); w_lq_ntok.release(); w_lq_cls.release(); w_big_n.release();
         w_sort_hist.release(); w_big_dst.release(); w_big_src.release(); w_scan_part.release();
         w_idA.release(); w_rkA.release(); w_idB.release(); w_rkB.release(); w_aux1.release(); w_aux2.release();
-        w_flag.release();
+        w_flag.release(); w_pack.release();
         if (stage.p) cudaFreeHost(stage.p);
         stage.p = nullptr; stage.cap = 0;
+        if (stage_out.p) cudaFreeHost(stage_out.p);
+        stage_out.p = nullptr; stage_out.cap = 0;
         long_cap = miss_cap = mres_cap = slow_cap = 0;
     }
     void destroy() {
@@ -185,6 +232,7 @@ struct Slot {
         if (stream) cudaStreamDestroy(stream);
         if (side) cudaStreamDestroy(side);
         if (side2) cudaStreamDestroy(side2);
+        if (up) cudaStreamDestroy(up);
     }
 };
 
@@ -231,6 +279,8 @@ struct b200bpe {
     uint32_t last_launches = 0;
     size_t chunk_bytes = 64u << 20; bool chunk_forced = false;
     int copy_threads = 4;
+    TaskPool *pool = nullptr;        // helper threads (created with the first host-path call)
+    int pack_bits = 0;               // host path: tokens cross PCIe as fields of this many bits (0: plain u32)
     bool mid_group = true;           // 17..1024-byte pieces: group-of-lanes kernels (need ranks < 2^22)
     bool pmerge = true;              // 129..1024-byte pieces: segmented parallel merge (needs ranks < 2^22); off: the group-of-lanes kernels
     int pmerge_min_cls = 3;          // shortest length class the parallel merge takes (3: 129..256 bytes; 0: everything from 17 bytes)
@@ -425,7 +475,16 @@ extern "C" int b200bpe_create_multi(const uint8_t *tok_bytes, const uint64_t *to
     h->mid_group = H.max_rank < MIDG_MAX_RANK && env_long("B200BPE_MID_GROUP", 1, 0, 1) != 0;
     h->pmerge = h->mid_group && env_long("B200BPE_PMERGE", 1, 0, 1) != 0;
     h->pmerge_min_cls = (int)env_long("B200BPE_PMERGE_MIN_CLS", 3, 0, 3);
-    h->copy_threads = (int)env_long("B200BPE_COPY_THREADS", std::max(1u, std::min(8u, std::thread::hardware_concurrency() / 4)), 1, 64);
+    h->copy_threads = (int)env_long("B200BPE_COPY_THREADS", std::max(1u, std::min(16u, std::thread::hardware_concurrency() / 4)), 1, 64);
+    {   // tokens return over PCIe as bit fields just wide enough for the largest id (17 bits for cl100k, 18 for o200k, 16 for
+        // r50k / p50k instead of 32): the return traffic shares the link with the text going up
+        uint32_t max_id = H.max_rank;
+        for (uint32_t r : h->special_rank) max_id = std::max(max_id, r);
+        int bits = 1;
+        while (bits < 32 && (max_id >> bits)) bits++;
+        bits = std::max(bits, 8);
+        h->pack_bits = (bits <= 24 && env_long("B200BPE_PACK", 0, 0, 1)) ? bits : 0;   // opt-in: see DESIGN 4 (measured: no gain)
+    }
     h->table_bytes[0] = H.piece_tab.size() * sizeof(U4);
     h->table_bytes[1] = H.pair_tab.size() * sizeof(U4) + 65536 * 4 + 1024;
     h->table_bytes[2] = H.long_tab.size() * sizeof(U4) + H.long_blob.size();
@@ -445,6 +504,7 @@ static void engine_teardown(b200bpe *h) {
     DeviceGuard guard;
     for (auto *d : h->devs) devctx_destroy(d);
     for (auto &b : h->pinned_pool) cudaFreeHost(b.p);
+    delete h->pool;
     delete h;
 }
 
@@ -851,25 +911,66 @@ static void host_worker(HostJob *J, int dev_index, size_t first, size_t step) {
     const size_t n_chunks = J->cut.size() - 1;
     std::vector<size_t> mine;
     for (size_t c = first; c < n_chunks; c += step) mine.push_back(c);
+    // ---- packed return path: a thread of its own waits for the packed tokens of a chunk to land in pinned staging and has
+    //      the pool widen them into the result, so that neither the device pipeline nor this worker waits for host memory
+    struct UnpackJob { Slot *S; cudaEvent_t ev; const uint8_t *src; uint32_t *dst; uint64_t n; };
+    std::mutex uq_mu; std::condition_variable uq_cv; std::deque<UnpackJob> uq; bool uq_stop = false;
+    const int pack_bits = (h->pack_bits && !J->single_piece) ? h->pack_bits : 0;
+    std::thread unpacker;
+    auto stop_unpacker = [&] {
+        if (!unpacker.joinable()) return;
+        { std::lock_guard<std::mutex> lk(uq_mu); uq_stop = true; }
+        uq_cv.notify_all();
+        unpacker.join();                                         // drains the queue first
+    };
     auto bail = [&](int rc) {
         if (rc) J->set_error(rc);
         for (size_t k = 0; k < mine.size(); k++) { long long m1 = -1; J->count[mine[k]].compare_exchange_strong(m1, 0); }   // never leave a waiter spinning
-        for (int i = 0; i < DevCtx::N_SLOTS; i++) cudaStreamSynchronize(D->slots[i].stream);
+        for (int i = 0; i < DevCtx::N_SLOTS; i++) { cudaStreamSynchronize(D->slots[i].up); cudaStreamSynchronize(D->slots[i].stream); }
+        stop_unpacker();                                         // after the copies: everything queued is widened before we return
     };
     if (mine.empty()) return;
     if (cudaSetDevice(D->device) != cudaSuccess) { fail(B200BPE_ECUDA, "cudaSetDevice failed"); return bail(B200BPE_ECUDA); }
+    if (pack_bits) unpacker = std::thread([&] {
+        cudaSetDevice(D->device);
+        for (;;) {
+            UnpackJob job;
+            {
+                std::unique_lock<std::mutex> lk(uq_mu);
+                uq_cv.wait(lk, [&] { return uq_stop || !uq.empty(); });
+                if (uq.empty()) return;
+                job = uq.front(); uq.pop_front();
+            }
+            if (cudaEventSynchronize(job.ev) == cudaSuccess)
+                pool_for(h->pool, (size_t)job.n, (size_t)1 << 19, [&](size_t lo, size_t hi) { unpack_tokens(job.src, job.dst, lo, hi, pack_bits); });
+            else J->set_error(fail(B200BPE_ECUDA, "cudaEventSynchronize failed in the token unpacker"));
+            job.S->stage_out_busy.store(0);
+        }
+    });
     const uint64_t *doc_off = J->doc_off;
     auto slot_of = [&](size_t k) -> Slot & { return D->slots[k % DevCtx::N_SLOTS]; };
 
+    // Upload of chunk k into its slot.  Pinned caller memory: on the slot's own stream, i.e. behind the download of the
+    // slot's previous chunk -- measured better than letting uploads run free (free-running uploads and downloads fight for
+    // the link: 38.8 vs 41.4 GB/s end to end).  Pageable caller memory: helper threads fill a pinned block quarter by
+    // quarter and the quarters go up on the slot's UPLOAD stream, which only waits for the kernels (ev[4]) of the slot's
+    // previous chunk, so that the host never sits behind a download (18 -> 22 GB/s).
     auto enqueue_h2d = [&](size_t k) -> int {
         Slot &S = slot_of(k);
         const size_t c = mine[k];
-        CUDA_TRY(cudaStreamSynchronize(S.stream));               // slot free again (its chunk k-3 fully drained)
         const uint64_t lo = J->cut[c], hi = J->cut[c + 1], b0 = doc_off[lo], nb = doc_off[hi] - b0, nd = hi - lo;
+        const bool staged = J->pageable && nb;
+        cudaStream_t us = staged ? S.up : S.stream;
+        if (!staged || S.w_text.cap < (size_t)nb + 64 || S.w_docoff.cap < (size_t)nd + 2 || S.w_tokoff.cap < (size_t)nd + 2 ||
+            S.w_out.cap < (size_t)nb + 64)
+            CUDA_TRY(cudaStreamSynchronize(S.stream));           // slot free again (or a buffer has to grow: nothing may be in flight)
+        else if (k >= (size_t)DevCtx::N_SLOTS) CUDA_TRY(cudaStreamWaitEvent(S.up, S.ev[4], 0));
         CUDA_TRY(S.w_text.ensure((size_t)nb + 64)); CUDA_TRY(S.w_docoff.ensure((size_t)nd + 2));
         CUDA_TRY(S.w_tokoff.ensure((size_t)nd + 2)); CUDA_TRY(S.w_out.ensure((size_t)nb + 64));
         const uint8_t *src = J->text + b0;
-        if (J->pageable && nb) {                                 // pageable caller memory: through a pinned staging block
+        CUDA_TRY(cudaEventRecord(S.ev[5], us));
+        if (staged) {
+            CUDA_TRY(cudaStreamSynchronize(S.up));               // the block's previous upload has left it
             if (S.stage.cap < nb) {
                 if (S.stage.p) cudaFreeHost(S.stage.p);
                 S.stage.p = nullptr; S.stage.cap = 0;
@@ -877,14 +978,18 @@ static void host_worker(HostJob *J, int dev_index, size_t first, size_t step) {
                 CUDA_TRY(cudaHostAlloc(&S.stage.p, want, cudaHostAllocPortable));
                 S.stage.cap = want;
             }
-            parallel_memcpy(S.stage.p, src, (size_t)nb, h->copy_threads);
-            src = (const uint8_t *)S.stage.p;
-        }
-        CUDA_TRY(cudaEventRecord(S.ev[5], S.stream));
-        if (nb) CUDA_TRY(cudaMemcpyAsync(S.w_text.p, src, nb, cudaMemcpyHostToDevice, S.stream));
-        CUDA_TRY(cudaMemcpyAsync(S.w_docoff.p, doc_off + lo, (nd + 1) * 8, cudaMemcpyHostToDevice, S.stream));
-        if (b0) add_offset_kernel<<<(unsigned)((nd + 1 + 255) / 256), 256, 0, S.stream>>>(S.w_docoff.p, nd + 1, -(long long)b0);
-        CUDA_TRY(cudaEventRecord(S.ev[6], S.stream));
+            uint8_t *stg = (uint8_t *)S.stage.p;
+            const size_t group = std::max<size_t>((((size_t)nb / 4) + 4095) & ~(size_t)4095, (size_t)4 << 20);
+            for (size_t g0 = 0; g0 < (size_t)nb; g0 += group) {
+                const size_t len = std::min(group, (size_t)nb - g0);
+                pool_for(h->pool, len, (size_t)1 << 20, [&](size_t lo, size_t hi) { memcpy(stg + g0 + lo, src + g0 + lo, hi - lo); });
+                CUDA_TRY(cudaMemcpyAsync(S.w_text.p + g0, stg + g0, len, cudaMemcpyHostToDevice, us));
+            }
+        } else if (nb) CUDA_TRY(cudaMemcpyAsync(S.w_text.p, src, nb, cudaMemcpyHostToDevice, us));
+        CUDA_TRY(cudaMemcpyAsync(S.w_docoff.p, doc_off + lo, (nd + 1) * 8, cudaMemcpyHostToDevice, us));
+        if (b0) add_offset_kernel<<<(unsigned)((nd + 1 + 255) / 256), 256, 0, us>>>(S.w_docoff.p, nd + 1, -(long long)b0);
+        CUDA_TRY(cudaEventRecord(S.ev[6], us));
+        if (staged) CUDA_TRY(cudaStreamWaitEvent(S.stream, S.ev[6], 0));     // the slot's pipeline starts when its text has arrived
         return B200BPE_OK;
     };
     auto args_of = [&](size_t k) {
@@ -933,7 +1038,25 @@ static void host_worker(HostJob *J, int dev_index, size_t first, size_t step) {
         if (token_base) add_offset_kernel<<<(unsigned)((nd + 1 + 255) / 256), 256, 0, S.stream>>>(S.w_tokoff.p, nd + 1, (long long)token_base);
         CUDA_TRY(cudaEventRecord(S.ev[5], S.stream));
         CUDA_TRY(cudaMemcpyAsync((uint64_t *)J->r->off.p + lo, S.w_tokoff.p, (nd + 1) * 8, cudaMemcpyDeviceToHost, S.stream));
-        if (nt) CUDA_TRY(cudaMemcpyAsync((uint32_t *)J->r->tok.p + token_base, S.w_out.p, nt * 4, cudaMemcpyDeviceToHost, S.stream));
+        if (nt && pack_bits) {
+            const unsigned long long n_words = (nt * (uint64_t)pack_bits + 31) / 32;
+            const size_t bytes = (size_t)n_words * 4;
+            CUDA_TRY(S.w_pack.ensure((size_t)n_words + 4));
+            while (S.stage_out_busy.load()) std::this_thread::yield();        // the slot's previous chunk is still being widened
+            if (S.stage_out.cap < bytes + 16) {
+                if (S.stage_out.p) cudaFreeHost(S.stage_out.p);
+                S.stage_out.p = nullptr; S.stage_out.cap = 0;
+                const size_t want = bytes + bytes / 4 + 4096;
+                CUDA_TRY(cudaHostAlloc(&S.stage_out.p, want, cudaHostAllocPortable));
+                S.stage_out.cap = want;
+            }
+            pack_tokens_kernel<<<(unsigned)((n_words + 255) / 256), 256, 0, S.stream>>>(S.w_out.p, nt, pack_bits, S.w_pack.p, n_words);
+            CUDA_TRY(cudaMemcpyAsync(S.stage_out.p, S.w_pack.p, bytes, cudaMemcpyDeviceToHost, S.stream));
+            CUDA_TRY(cudaEventRecord(S.ev[14], S.stream));
+            S.stage_out_busy.store(1);
+            { std::lock_guard<std::mutex> lk(uq_mu); uq.push_back({&S, S.ev[14], (const uint8_t *)S.stage_out.p, (uint32_t *)J->r->tok.p + token_base, nt}); }
+            uq_cv.notify_one();
+        } else if (nt) CUDA_TRY(cudaMemcpyAsync((uint32_t *)J->r->tok.p + token_base, S.w_out.p, nt * 4, cudaMemcpyDeviceToHost, S.stream));
         CUDA_TRY(cudaEventRecord(S.ev[6], S.stream));
         for (int i = 0; i < 5; i++) sum_ms[i] += S.last_ms[i];
         sum_ms[7] += S.last_ms[7]; sum_ms[8] += S.last_ms[8]; sum_ms[5] += h2d; launches += S.last_launches;
@@ -963,6 +1086,8 @@ static int encode_host(b200bpe *h, const uint8_t *text, const uint64_t *doc_off,
     const uint64_t n_bytes = doc_off[n_docs];
     if (doc_off[0] != 0) return fail(B200BPE_EINVAL, "document offsets must start at 0");
     const int n_dev = (int)h->devs.size();
+    if (!h->pool) h->pool = new TaskPool();
+    h->pool->ensure(h->copy_threads);
     // ---- chunk plan: document ranges [lo, hi) ------------------------------------------------
     size_t chunk = h->chunk_bytes;
     if (!h->chunk_forced && n_dev > 1) chunk = std::min<size_t>(64u << 20, std::max<size_t>(8u << 20, (size_t)(n_bytes / (4 * (uint64_t)n_dev))));

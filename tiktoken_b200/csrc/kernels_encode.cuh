@@ -511,3 +511,18 @@ __global__ void __launch_bounds__(256) big_copy_kernel(TileParams p) {
             p.out[dst + x] = p.ltok[src + x];
     }
 }
+
+// host path: tokens -> fields of `bits` bits, little-endian bit order (token i occupies bits [i*bits, (i+1)*bits) of the
+// stream); one output word per thread, assembled from the 2..5 tokens that overlap it.  Halves the PCIe return traffic.
+__global__ void __launch_bounds__(256) pack_tokens_kernel(const uint32_t *__restrict__ tok, unsigned long long n, int bits,
+                                                         uint32_t *__restrict__ out, unsigned long long n_words) {
+    const unsigned long long w = blockIdx.x * 256ull + threadIdx.x;
+    if (w >= n_words) return;
+    const unsigned long long bit0 = w * 32ull;
+    unsigned long long i = bit0 / (unsigned)bits;
+    int sh = (int)(bit0 - i * (unsigned)bits);             // bits of token i that lie below this word
+    unsigned long long acc = i < n ? ((unsigned long long)ld_stream_u32(tok + i) >> sh) : 0ull;
+    int have = bits - sh;
+    for (i++; have < 32; i++, have += bits) acc |= (i < n ? (unsigned long long)ld_stream_u32(tok + i) : 0ull) << have;
+    out[w] = (uint32_t)acc;
+}

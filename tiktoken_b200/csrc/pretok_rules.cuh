@@ -119,6 +119,61 @@ B2_HD bool boundary_r50k(const T &t, int64_t pos) {
     return !(is_other(p) || p == C_SP);          // "other", incl. an apostrophe starting alt. 1
 }
 
+B2_HD int b2_ctz32(uint32_t x) {
+#if defined(__CUDA_ARCH__)
+    return __ffs((int)x) - 1;
+#else
+    return __builtin_ctz(x);
+#endif
+}
+B2_HD int b2_ctz64(uint64_t x) {
+#if defined(__CUDA_ARCH__)
+    return __ffsll((long long)x) - 1;
+#else
+    return __builtin_ctzll(x);
+#endif
+}
+// What lies ahead of the whitespace scalar at `pos` in its run of whitespace: 1 = a CR/LF, 2 = the end of the document,
+// 0 = a non-whitespace scalar.  Runs of ASCII whitespace are walked eight bytes at a time (SWAR on one aligned 64-bit word
+// + the doc-start bits of its eight positions); anything else takes the scalar-by-scalar accessor.  (The mixed-script
+// workload has whitespace runs of hundreds of bytes behind line ends: the per-scalar walk made the listed positions as
+// expensive as the whole bit-parallel kernel.)
+template <class T>
+B2_HD int ws_run_ahead(const T &t, int64_t pos) {
+    int64_t q = t.next(pos);
+    for (;;) {
+        if (q < 0) return 2;
+        const int64_t a = q & ~(int64_t)7;
+        const uint64_t w = *reinterpret_cast<const uint64_t *>(t.text + a);
+        const uint64_t H = 0x8080808080808080ull, L = 0x0101010101010101ull;
+        const uint64_t y = w & ~H, hi = w & H;
+        const uint64_t ge9 = (y + (0x80 - 0x09) * L) & H, geE = (y + (0x80 - 0x0E) * L) & H;
+        const uint64_t eq20 = ~(((y ^ (0x20 * L)) + (0x7F * L))) & H;
+        const uint64_t eqA = ~(((y ^ (0x0A * L)) + (0x7F * L))) & H, eqD = ~(((y ^ (0x0D * L)) + (0x7F * L))) & H;
+        const uint64_t nl = (eqA | eqD) & ~hi;                               // bit 7 of the byte lanes that hold CR / LF
+        const uint64_t ws = ((ge9 & ~geE) | eq20) & ~hi;                     // ... ASCII whitespace (CR / LF included)
+        uint32_t d = (t.dbits[a >> 5] >> (a & 31)) & 0xFFu;                  // documents that start at a .. a+7
+        const int k0 = (int)(q - a);
+        d &= ~((2u << k0) - 1u);                                             // only AFTER q: q itself is inside the document
+        uint64_t stop = ~ws & H;                                             // lanes that are not ASCII whitespace
+        for (uint32_t dd = d; dd; dd &= dd - 1) stop |= 0x80ull << (8 * (b2_ctz32(dd)));
+        if (a + 8 > t.n) for (int k = (int)(t.n - a); k < 8; k++) stop |= 0x80ull << (8 * (k < 0 ? 0 : k));
+        const uint64_t from = ~0ull << (8 * k0);
+        const uint64_t ev = (stop | nl) & from;
+        if (!ev) { q = a + 8; if (q >= t.n) return 2; if (t.doc_start(q)) return 2; continue; }
+        const int k = b2_ctz64(ev) >> 3;
+        const uint64_t lane = 0x80ull << (8 * k);
+        if (!(stop & lane)) return 1;                                        // CR / LF first
+        if (a + k >= t.n || ((d >> k) & 1u)) return 2;                       // the document ends first
+        if (!(hi & lane)) return 0;                                          // an ASCII non-whitespace byte
+        q = a + k;                                                           // non-ASCII: one scalar through the accessor
+        const int cq = t.cls(q);
+        if (cq == C_NL) return 1;
+        if (!is_ws(cq)) return 0;
+        q = t.next(q);
+    }
+}
+
 template <class T>
 B2_HD bool boundary_cl100k(const T &t, int64_t pos) {
     const int c = t.cls(pos);
@@ -151,15 +206,7 @@ B2_HD bool boundary_cl100k(const T &t, int64_t pos) {
         // previous scalar is CR/LF: `\s++$` / `\s*[\r\n]` swallow pos iff the run reaches the
         // document end or has another CR/LF ahead -- unless the CR/LFs before pos were taken by
         // a preceding `[^\s\p{L}\p{N}]++[\r\n]*+` piece, in which case a fresh match starts here.
-        bool swallowed = false;
-        for (int64_t q = pos;;) {
-            q = t.next(q);
-            if (q < 0) { swallowed = true; break; }
-            int cq = t.cls(q);
-            if (cq == C_NL) { swallowed = true; break; }
-            if (!is_ws(cq)) break;
-        }
-        if (!swallowed) return true;
+        if (ws_run_ahead(t, pos) == 0) return true;
         int64_t q = pp;
         while (q >= 0 && t.cls(q) == C_NL) q = t.prev(q);
         return q >= 0 && is_other(t.cls(q));
@@ -346,15 +393,7 @@ B2_HD bool boundary_o200k(const T &t, int64_t pos) {
         }
         // o200k has no `\s++$`: `\s*[\r\n]+` is tried first, so only a CR/LF further on in the run
         // (not the document end) keeps pos inside the piece of the preceding CR/LF.
-        bool swallowed = false;
-        for (int64_t q = pos;;) {
-            q = t.next(q);
-            if (q < 0) break;
-            int cq = t.cls(q);
-            if (cq == C_NL) { swallowed = true; break; }
-            if (!is_ws(cq)) break;
-        }
-        if (!swallowed) return true;
+        if (ws_run_ahead(t, pos) != 1) return true;
         return o200k_xm_state(t, pp).st == XS_TRAIL;
     }
     if (c == C_NL) {
