@@ -50,9 +50,18 @@ __device__ __forceinline__ U4 ldg_u4(const U4 *p) {
     uint4 v = __ldg(reinterpret_cast<const uint4 *>(p));
     U4 r; r.x = v.x; r.y = v.y; r.z = v.z; r.w = v.w; return r;
 }
+// both 16-byte halves of a 32-byte table slot / bucket with ONE 256-bit load (sm_100: LDG.E.256).  The probe and merge
+// kernels are bound by L1TEX wavefronts (ncu: l1tex throughput 80-88 %): a lane-divergent load costs one wavefront per
+// lane whatever its width, so one 32-byte load per probe instead of two 16-byte ones halves the global part.
+__device__ __forceinline__ void ldg_u4x2(const U4 *p, U4 &a, U4 &b) {
+    asm("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+        : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w) : "l"(p));
+}
+#define B2_LDG_U4X2(p, a, b) b2bpe::ldg_u4x2(p, a, b)
 #else
 #define B2_LDG_U4(p) (*(p))
 #define B2_LDG_U32(p) (*(p))
+#define B2_LDG_U4X2(p, a, b) do { (a) = (p)[0]; (b) = (p)[1]; } while (0)
 #endif
 
 B2_HD uint32_t pair_hash(uint32_t a, uint32_t b) {
@@ -96,7 +105,7 @@ B2_HD uint64_t long_hash_init(uint64_t len) { return len * 0xC2B2AE3D27D4EB4Full
 B2_HD uint32_t pair_lookup(const DevTables &T, uint32_t a, uint32_t b) {
     uint32_t s = pair_hash(a, b) & T.pair_mask;
     for (;;) {
-        const U4 e0 = B2_LDG_U4(T.pair_tab + 2 * s), e1 = B2_LDG_U4(T.pair_tab + 2 * s + 1);
+        U4 e0, e1; B2_LDG_U4X2(T.pair_tab + 2 * s, e0, e1);
         if (e0.x == a && e0.y == b) return e0.z;
         if (e1.x == a && e1.y == b) return e1.z;
         if (e1.x == 0xFFFFFFFFu) return RANK_MAX;          // slots fill in order: a free second slot ends the chain
@@ -109,19 +118,20 @@ B2_HD uint32_t pair_lookup(const DevTables &T, uint32_t a, uint32_t b) {
 B2_HD void pair_lookup2(const DevTables &T, uint32_t a1, uint32_t b1, uint32_t a2, uint32_t b2, uint32_t &r1,
                         uint32_t &r2) {
     uint32_t s1 = pair_hash(a1, b1) & T.pair_mask, s2 = pair_hash(a2, b2) & T.pair_mask;
-    U4 e10 = B2_LDG_U4(T.pair_tab + 2 * s1), e11 = B2_LDG_U4(T.pair_tab + 2 * s1 + 1);
-    U4 e20 = B2_LDG_U4(T.pair_tab + 2 * s2), e21 = B2_LDG_U4(T.pair_tab + 2 * s2 + 1);
+    U4 e10, e11, e20, e21;
+    B2_LDG_U4X2(T.pair_tab + 2 * s1, e10, e11);
+    B2_LDG_U4X2(T.pair_tab + 2 * s2, e20, e21);
     for (;;) {
         if (e10.x == a1 && e10.y == b1) { r1 = e10.z; break; }
         if (e11.x == a1 && e11.y == b1) { r1 = e11.z; break; }
         if (e11.x == 0xFFFFFFFFu) { r1 = RANK_MAX; break; }
-        s1 = (s1 + 1) & T.pair_mask; e10 = B2_LDG_U4(T.pair_tab + 2 * s1); e11 = B2_LDG_U4(T.pair_tab + 2 * s1 + 1);
+        s1 = (s1 + 1) & T.pair_mask; B2_LDG_U4X2(T.pair_tab + 2 * s1, e10, e11);
     }
     for (;;) {
         if (e20.x == a2 && e20.y == b2) { r2 = e20.z; break; }
         if (e21.x == a2 && e21.y == b2) { r2 = e21.z; break; }
         if (e21.x == 0xFFFFFFFFu) { r2 = RANK_MAX; break; }
-        s2 = (s2 + 1) & T.pair_mask; e20 = B2_LDG_U4(T.pair_tab + 2 * s2); e21 = B2_LDG_U4(T.pair_tab + 2 * s2 + 1);
+        s2 = (s2 + 1) & T.pair_mask; B2_LDG_U4X2(T.pair_tab + 2 * s2, e20, e21);
     }
 }
 
@@ -129,8 +139,7 @@ B2_HD void pair_lookup2(const DevTables &T, uint32_t a1, uint32_t b1, uint32_t a
 B2_HD uint32_t piece_lookup16(const DevTables &T, uint64_t k0, uint64_t k1, uint32_t len) {
     uint32_t s = (uint32_t)piece_hash(k0, k1, len) & T.piece_mask;
     for (;;) {
-        const U4 m = B2_LDG_U4(T.piece_tab + 2 * s + 1);      // both halves of the 32-byte slot: one sector
-        const U4 k = B2_LDG_U4(T.piece_tab + 2 * s);
+        U4 k, m; B2_LDG_U4X2(T.piece_tab + 2 * s, k, m);          // both halves of the 32-byte slot: one sector, one load
         if (m.x == 0) return RANK_MAX;
         if (m.x == len && k.x == (uint32_t)k0 && k.y == (uint32_t)(k0 >> 32) && k.z == (uint32_t)k1 &&
             k.w == (uint32_t)(k1 >> 32))
@@ -296,8 +305,8 @@ B2_HD uint32_t merge_short_conv(const DevTables &T, ByteFn byte_at, int n, int n
         bool p1 = need_r, p2 = need_l;
         while (B2_ANY(group, p1 || p2)) {
             U4 e0 = {0, 0, 0, 0}, e1 = {0, 0, 0, 0}, f0 = {0, 0, 0, 0}, f1 = {0, 0, 0, 0};
-            if (p1) { e0 = B2_LDG_U4(T.pair_tab + 2 * s1); e1 = B2_LDG_U4(T.pair_tab + 2 * s1 + 1); }
-            if (p2) { f0 = B2_LDG_U4(T.pair_tab + 2 * s2); f1 = B2_LDG_U4(T.pair_tab + 2 * s2 + 1); }
+            if (p1) B2_LDG_U4X2(T.pair_tab + 2 * s1, e0, e1);
+            if (p2) B2_LDG_U4X2(T.pair_tab + 2 * s2, f0, f1);
             if (p1) {
                 if (e0.x == a1 && e0.y == b1) { r1 = e0.z; p1 = false; }
                 else if (e1.x == a1 && e1.y == b1) { r1 = e1.z; p1 = false; }
@@ -413,8 +422,8 @@ B2_HD void merge_mid_conv(const DevTables &T, int n, int n_max, unsigned group, 
         bool p1 = need_r, p2 = need_l;
         while (B2_ANY(group, p1 || p2)) {
             U4 e0 = {0, 0, 0, 0}, e1 = {0, 0, 0, 0}, f0 = {0, 0, 0, 0}, f1 = {0, 0, 0, 0};
-            if (p1) { e0 = B2_LDG_U4(T.pair_tab + 2 * s1); e1 = B2_LDG_U4(T.pair_tab + 2 * s1 + 1); }
-            if (p2) { f0 = B2_LDG_U4(T.pair_tab + 2 * s2); f1 = B2_LDG_U4(T.pair_tab + 2 * s2 + 1); }
+            if (p1) B2_LDG_U4X2(T.pair_tab + 2 * s1, e0, e1);
+            if (p2) B2_LDG_U4X2(T.pair_tab + 2 * s2, f0, f1);
             if (p1) {
                 if (e0.x == a1 && e0.y == b1) { r1 = e0.z; p1 = false; }
                 else if (e1.x == a1 && e1.y == b1) { r1 = e1.z; p1 = false; }

@@ -160,7 +160,7 @@ __global__ void __launch_bounds__(ENC_WARPS * 32) probe_kernel(TileParams p, Dev
                 if (m.x == 0) break;
                 if (m.x == (uint32_t)len && k.x == a0 && k.y == a1 && k.z == a2 && k.w == a3) { r = m.y; break; }
                 s = (s + 1) & T.piece_mask;
-                m = B2_LDG_U4(T.piece_tab + 2 * s + 1); k = B2_LDG_U4(T.piece_tab + 2 * s);
+                B2_LDG_U4X2(T.piece_tab + 2 * s, k, m);
             }
             if (r != RANK_MAX) { st_stream_u32(slot + i, r); cnt++; }
             else S.miss[atomicAdd(&S.nmiss, 1u)] = (uint16_t)i;
@@ -172,8 +172,8 @@ __global__ void __launch_bounds__(ENC_WARPS * 32) probe_kernel(TileParams p, Dev
             const int needB = prep(i + 32, lenB, b0, b1, b2, b3);
             uint32_t sA = 0, sB = 0;
             U4 mA = {0, 0, 0, 0}, kA = {0, 0, 0, 0}, mB = {0, 0, 0, 0}, kB = {0, 0, 0, 0};
-            if (needA) { sA = piece_hash4(a0, a1, a2, a3, (uint32_t)lenA) & T.piece_mask; mA = B2_LDG_U4(T.piece_tab + 2 * sA + 1); kA = B2_LDG_U4(T.piece_tab + 2 * sA); }
-            if (needB) { sB = piece_hash4(b0, b1, b2, b3, (uint32_t)lenB) & T.piece_mask; mB = B2_LDG_U4(T.piece_tab + 2 * sB + 1); kB = B2_LDG_U4(T.piece_tab + 2 * sB); }
+            if (needA) { sA = piece_hash4(a0, a1, a2, a3, (uint32_t)lenA) & T.piece_mask; B2_LDG_U4X2(T.piece_tab + 2 * sA, kA, mA); }
+            if (needB) { sB = piece_hash4(b0, b1, b2, b3, (uint32_t)lenB) & T.piece_mask; B2_LDG_U4X2(T.piece_tab + 2 * sB, kB, mB); }
             if (needA) finish(i, lenA, a0, a1, a2, a3, sA, mA, kA);
             if (needB) finish(i + 32, lenB, b0, b1, b2, b3, sB, mB, kB);
         }

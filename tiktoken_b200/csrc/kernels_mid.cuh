@@ -177,7 +177,7 @@ __device__ void midg_class(const uint8_t *__restrict__ text, const DevTables &T,
                 uint32_t sidx = pair_hash(a, b) & T.pair_mask;
                 while (__any_sync(0xFFFFFFFFu, pr)) {
                     if (pr) {
-                        const U4 e0 = B2_LDG_U4(T.pair_tab + 2 * sidx), e1 = B2_LDG_U4(T.pair_tab + 2 * sidx + 1);
+                        U4 e0, e1; B2_LDG_U4X2(T.pair_tab + 2 * sidx, e0, e1);
                         if (e0.x == a && e0.y == b) { r = e0.z; pr = false; }
                         else if (e1.x == a && e1.y == b) { r = e1.z; pr = false; }
                         else if (e1.x == 0xFFFFFFFFu) pr = false;
