@@ -169,8 +169,8 @@ void unpack_tokens(const uint8_t *src, uint32_t *dst, size_t lo, size_t hi, int 
 // three slots in flight per device (H2D of chunk c+1, kernels of chunk c, D2H of chunk c-1).
 struct Slot {
     DevBuf<uint8_t> w_text; DevBuf<unsigned long long> w_docoff, w_tokoff, w_sub_base;
-    DevBuf<uint32_t> w_ptok, w_mres, w_mq_pos, w_mq_roff, w_mq_dst, w_doc_tiles, w_sub_count; DevBuf<uint8_t> w_mq_len, w_mq_cnt;
-    DevBuf<uint4> w_mq_key, w_mq_skey, w_mq_smeta;
+    DevBuf<uint32_t> w_ptok, w_mres, w_mq_pos, w_mq_roff, w_doc_tiles, w_sub_count; DevBuf<uint8_t> w_mq_len;
+    DevBuf<uint4> w_mq_key, w_mq_skey, w_mq_smeta, w_mq_rec;
     DevBuf<uint32_t> w_dbits, w_pbits, w_psum, w_sfd, w_lidx, w_out, w_ltok, w_hbits, w_ibits, w_sbits, w_cbits, w_slow;
     DevBuf<unsigned long long> w_lq_start, w_lq_off; DevBuf<unsigned int> w_lq_len, w_lq_ntok, w_lq_cls, w_big_n, w_sort_hist;
     DevBuf<unsigned long long> w_big_dst, w_big_src, w_scan_part;
@@ -209,8 +209,8 @@ struct Slot {
     }
     void release_workspace() {
         w_text.release(); w_docoff.release(); w_tokoff.release(); w_sub_base.release();
-        w_ptok.release(); w_mres.release(); w_mq_pos.release(); w_mq_roff.release(); w_mq_dst.release(); w_doc_tiles.release(); w_sub_count.release();
-        w_mq_len.release(); w_mq_cnt.release(); w_mq_key.release(); w_mq_skey.release(); w_mq_smeta.release();
+        w_ptok.release(); w_mres.release(); w_mq_pos.release(); w_mq_roff.release(); w_doc_tiles.release(); w_sub_count.release();
+        w_mq_len.release(); w_mq_rec.release(); w_mq_key.release(); w_mq_skey.release(); w_mq_smeta.release();
         w_dbits.release(); w_pbits.release(); w_psum.release(); w_sfd.release(); w_lidx.release(); w_out.release(); w_ltok.release();
         w_hbits.release(); w_ibits.release(); w_sbits.release(); w_cbits.release(); w_slow.release(); w_spflags.release();
         w_lq_start.release(); w_lq_off.release(); w_lq_len.release(); w_lq_ntok.release(); w_lq_cls.release(); w_big_n.release();
@@ -579,8 +579,8 @@ static int enqueue_pipeline(b200bpe *h, DevCtx *D, Slot &S, const PipeArgs &a) {
         if (S.miss_cap < want_q) S.miss_cap = want_q;
         if (S.mres_cap < want_r) S.mres_cap = want_r;
         const size_t mcap = S.miss_cap;
-        CUDA_TRY(S.w_mq_pos.ensure(mcap)); CUDA_TRY(S.w_mq_roff.ensure(mcap)); CUDA_TRY(S.w_mq_dst.ensure(mcap));
-        CUDA_TRY(S.w_mq_len.ensure(mcap)); CUDA_TRY(S.w_mq_cnt.ensure(mcap));
+        CUDA_TRY(S.w_mq_pos.ensure(mcap)); CUDA_TRY(S.w_mq_roff.ensure(mcap)); CUDA_TRY(S.w_mq_rec.ensure(mcap));
+        CUDA_TRY(S.w_mq_len.ensure(mcap));
         CUDA_TRY(S.w_mq_key.ensure(mcap)); CUDA_TRY(S.w_mq_skey.ensure(mcap)); CUDA_TRY(S.w_mq_smeta.ensure(mcap));
         CUDA_TRY(S.w_mres.ensure(S.mres_cap + 64));
         CUDA_TRY(S.w_sort_hist.ensure((size_t)SORT_BLOCKS * 17 + 32));
@@ -708,8 +708,8 @@ static int enqueue_pipeline(b200bpe *h, DevCtx *D, Slot &S, const PipeArgs &a) {
         p.pbits = S.w_pbits.p; p.dbits = S.w_dbits.p; p.span_first_doc = S.w_sfd.p;
         p.doc_off = a.d_doc_off; p.n_docs = n_docs; p.q = q; p.lidx = S.w_lidx.p; p.ltok = S.w_ltok.p;
         p.ptok = S.w_ptok.p; p.mres = S.w_mres.p; p.sbits = sbits;
-        p.mq.key = S.w_mq_key.p; p.mq.pos = S.w_mq_pos.p; p.mq.roff = S.w_mq_roff.p; p.mq.len = S.w_mq_len.p; p.mq.cnt = S.w_mq_cnt.p;
-        p.mq.dst = S.w_mq_dst.p; p.doc_tiles = S.w_doc_tiles.p;
+        p.mq.key = S.w_mq_key.p; p.mq.pos = S.w_mq_pos.p; p.mq.roff = S.w_mq_roff.p; p.mq.len = S.w_mq_len.p; p.mq.rec = S.w_mq_rec.p;
+        p.doc_tiles = S.w_doc_tiles.p;
         p.mq.skey = S.w_mq_skey.p; p.mq.smeta = S.w_mq_smeta.p; p.mq.cap = (uint32_t)std::min<size_t>(S.miss_cap, 0xFFFFFFF0u);
         p.mq.mres_cap = S.mres_cap;
         p.sub_count = S.w_sub_count.p; p.sub_base = S.w_sub_base.p;
@@ -737,10 +737,9 @@ static int enqueue_pipeline(b200bpe *h, DevCtx *D, Slot &S, const PipeArgs &a) {
             gather_kernel<0><<<gather_grid, GATHER_WARPS * 32, 0, st>>>(p);
             gather_kernel<1><<<(unsigned)((n_docs + 1 + GATHER_WARPS - 1) / GATHER_WARPS), GATHER_WARPS * 32, 0, st>>>(p);
         } else gather_kernel<2><<<gather_grid, GATHER_WARPS * 32, 0, st>>>(p);
-        miss_copy_kernel<<<148 * 8, 256, 0, st>>>(p);
         big_copy_kernel<<<148 * 2, 256, 0, st>>>(p);
         finalize_kernel<<<1, 32, 0, st>>>(S.d_ctr, S.d_sticky, a.d_counts, n_docs);
-        launches += sparse_docs ? 13 : 12;
+        launches += sparse_docs ? 12 : 11;
     }
     CUDA_TRY(cudaEventRecord(S.ev[4], st));
     CUDA_TRY(cudaMemcpyAsync(S.h_ctr, S.d_ctr, sizeof(Counters), cudaMemcpyDeviceToHost, st));

@@ -26,8 +26,7 @@ struct MissQ {                // queue of pieces (2..16 bytes) that are not toke
     uint32_t *pos;            // byte offset of the piece
     uint32_t *roff;           // offset of its result region in mres (sum of lengths => tokens always fit)
     uint8_t *len;
-    uint8_t *cnt;             // tokens produced (written by miss_kernel)
-    uint32_t *dst;            // where its tokens go in the output (written by the gather, used by miss_copy_kernel)
+    uint4 *rec;               // result record (written by miss_kernel): {tokens produced, first three tokens}; the rest, if any, in mres
     uint4 *skey;              // keys sorted by piece length (so that a warp merges pieces of one length)
     uint4 *smeta;             // {queue index, roff, pos, len} in the same order
     uint32_t cap;             // capacity of the queue (entries)
@@ -310,16 +309,20 @@ __global__ void __launch_bounds__(MISS_WARPS * 32, MISS_MIN_BLOCKS) miss_kernel(
         const uint32_t mask = merge_short_conv(
             T, [&](int j) { return (bw[(j >> 2) * 32] >> (8 * (j & 3))) & 0xFFu; }, len, n_max, 0xFFFFFFFFu, id, rk);
         if (have) {
+            // the result record the gather reads: count + the first three tokens (97 % of the missed pieces end as <= 3
+            // tokens); longer results also go to mres.  One 16-byte store per piece instead of a token array + a count.
+            const uint32_t c = (uint32_t)__popc(mask);
+            uint32_t t[3] = {0, 0, 0}, k = 0; bool bad = false;
             uint32_t *dst = p.mres + meta.y;
-            uint32_t c = 0; bool bad = false;
-            for (uint32_t mm = mask; mm;) {
+            for (uint32_t mm = mask; mm; k++) {
                 const int j = __ffs(mm) - 1; mm &= mm - 1;
                 const uint32_t x = id[j];
                 bad |= x >= PSEUDO_BASE;
-                dst[c++] = x;
+                if (k == 0) t[0] = x; else if (k == 1) t[1] = x; else if (k == 2) t[2] = x;
+                if (c > 3) dst[k] = x;
             }
             if (bad) atomicOr(&p.ctr->err, ERR_NOBYTE);
-            p.mq.cnt[meta.x] = (uint8_t)c;
+            st_stream_u4(p.mq.rec + meta.x, make_uint4(c, t[0], t[1], t[2]));
             atomicAdd(&p.sub_count[meta.z >> 10], c);
         }
         __syncwarp();
@@ -438,7 +441,7 @@ __global__ void __launch_bounds__(GATHER_WARPS * 32, MODE ? 6 : 8) gather_kernel
     auto count_of = [&](uint32_t v) -> uint32_t {
         if (v == PT_EMPTY) return 0u;
         const uint32_t kind = v & PT_KIND, qi = v & PT_PAYLOAD;
-        return kind == 0 ? 1u : kind == PT_MISS ? (uint32_t)p.mq.cnt[qi] : p.q.ntok[qi];
+        return kind == 0 ? 1u : kind == PT_MISS ? __ldg(reinterpret_cast<const uint32_t *>(p.mq.rec + qi)) : p.q.ntok[qi];
     };
     uint32_t v0 = load_slot(0), v1 = load_slot(32);
     uint32_t n0 = count_of(v0);
@@ -454,7 +457,13 @@ __global__ void __launch_bounds__(GATHER_WARPS * 32, MODE ? 6 : 8) gather_kernel
         unsigned long long lsrc = 0;
         if (n) {
             if (kind == 0) st_stream_u32(p.out + k, v);
-            else if (kind == PT_MISS) p.mq.dst[qi] = (uint32_t)k;     // copied by miss_copy_kernel, one miss per lane
+            else if (kind == PT_MISS) {                               // the record is in the sector its count came from
+                const uint4 r = __ldg(p.mq.rec + qi);
+                st_stream_u32(p.out + k, r.y);
+                if (n > 1) st_stream_u32(p.out + k + 1, r.z);
+                if (n > 2) st_stream_u32(p.out + k + 2, r.w);
+                if (n > 3) { const uint32_t *src = p.mres + p.mq.roff[qi]; for (uint32_t x = 3; x < n; x++) st_stream_u32(p.out + k + x, src[x]); }
+            }
             else {
                 lsrc = p.q.start[qi];
                 if (n <= 32) for (uint32_t x = 0; x < n; x++) st_stream_u32(p.out + k + x, p.ltok[lsrc + x]);
@@ -487,17 +496,6 @@ __global__ void __launch_bounds__(GATHER_WARPS * 32, MODE ? 6 : 8) gather_kernel
                 while (d <= p.n_docs && p.doc_off[d] == pos) { p.tok_off[d] = tok; d++; }
             }
         }
-    }
-}
-
-// tokens of the missed pieces: mres -> their place in the output (found by the gather), one miss per lane
-__global__ void __launch_bounds__(256) miss_copy_kernel(TileParams p) {
-    const uint32_t n_miss = (p.ctr->err & ERR_MISSCAP) ? 0u : miss_count(p);
-    for (uint32_t qi = blockIdx.x * 256u + threadIdx.x; qi < n_miss; qi += gridDim.x * 256u) {
-        const uint32_t n = p.mq.cnt[qi];
-        const uint32_t *src = p.mres + p.mq.roff[qi];
-        uint32_t *dst = p.out + p.mq.dst[qi];
-        for (uint32_t x = 0; x < n; x++) st_stream_u32(dst + x, src[x]);
     }
 }
 
