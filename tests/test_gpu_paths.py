@@ -371,3 +371,66 @@ def test_trim_releases_and_the_engine_keeps_working():
     e._core_bpe.trim()                                   # work-spaces and pooled pinned blocks are gone, tables stay
     assert _same(e.encode_ordinary_packed(text, off), exp_t, exp_o)
     assert e.decode_bytes(exp_t) == text.tobytes()
+
+
+def test_reference_loaders_feed_the_engine(tmp_path, monkeypatch):
+    """`tiktoken/load.py` stays (north star): a `.tiktoken` file read by the reference's `load_tiktoken_bpe`, the same file
+    parsed in C (`Encoding.from_tiktoken_file`) and a gpt2-style data-gym pair (`vocab.bpe` + `encoder.json`,
+    `load.py:89-144`: single-byte ranks follow the printable-first order, not the byte values) all construct engines on
+    the GPU whose output equals the oracle's on the same ranks."""
+    import gzip
+    import json
+    import tiktoken.load as ref_load
+    import tiktoken_b200
+    monkeypatch.setenv("TIKTOKEN_CACHE_DIR", "")                                    # plain local reads, no cache directory
+    text = corpus.generate(corpus.ENGLISH, 5, 3 << 20)
+    off = corpus.docs_fixed(text, 40_000, at_space=True)[1]
+    special = {"<|endoftext|>": 50256}
+    # ---- .tiktoken: reference loader -> dict -> engine; C parser -> flat arrays -> engine
+    src = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "vocab", "r50k_like.tiktoken.gz")
+    path = str(tmp_path / "r50k_like.tiktoken")
+    with open(path, "wb") as f:
+        f.write(gzip.open(src).read())
+    ranks = ref_load.load_tiktoken_bpe(path)
+    o = _oracle(ranks, special, vu.R50K_PAT)
+    exp_t, exp_o = o.encode_ordinary_batch_np(text, off, CORES)
+    e_dict = tiktoken_b200.Encoding("by_ref_loader", pat_str=vu.R50K_PAT, mergeable_ranks=ranks, special_tokens=special)
+    e_file = tiktoken_b200.Encoding.from_tiktoken_file("by_c_parser", path, pat_str=vu.R50K_PAT, special_tokens=special)
+    assert _same(e_dict.encode_ordinary_packed(text, off), exp_t, exp_o)
+    assert _same(e_file.encode_ordinary_packed(text, off), exp_t, exp_o)
+    assert e_file.n_vocab == e_dict.n_vocab and e_file.decode_bytes(exp_t[:1000].tolist()) == e_dict.decode_bytes(exp_t[:1000].tolist())
+    # ---- data-gym: re-rank the single bytes the gpt2 way, write merges + encoder.json, read them back with the reference
+    order = [b for b in range(256) if chr(b).isprintable() and chr(b) != " "]
+    g2b, n = {chr(b): b for b in order}, 0
+    for b in range(256):
+        if b not in order:
+            order.append(b)
+            g2b[chr(256 + n)] = b
+            n += 1
+    b2g = {b: c for c, b in g2b.items()}
+    enc_gym = lambda bs: "".join(b2g[x] for x in bs)
+    small = {t: r for t, r in ranks.items() if len(t) == 1 or r < 256 + 6000}         # the first 6000 merges are enough here
+    gym = {bytes([b]): i for i, b in enumerate(order)}
+    merges, cur = [], dict(gym)
+    for tok, _ in sorted(((t, r) for t, r in small.items() if len(t) > 1), key=lambda x: x[1]):
+        parts = [bytes([x]) for x in tok]                                           # BPE of the token under the ranks so far -> its two parents
+        while len(parts) > 2:
+            best = min(range(len(parts) - 1), key=lambda i: (cur.get(parts[i] + parts[i + 1], 1 << 60), i))
+            if parts[best] + parts[best + 1] not in cur:
+                break
+            parts[best:best + 2] = [parts[best] + parts[best + 1]]
+        if len(parts) != 2:
+            continue                                                               # not reachable by merges of earlier tokens: leave it out
+        merges.append((parts[0], parts[1]))
+        cur[tok] = len(cur)
+    vocab_bpe, encoder_json = str(tmp_path / "vocab.bpe"), str(tmp_path / "encoder.json")
+    with open(vocab_bpe, "w", encoding="utf-8") as f:
+        f.write("#version: 0.2\n" + "".join(f"{enc_gym(a)} {enc_gym(b)}\n" for a, b in merges))
+    with open(encoder_json, "w", encoding="utf-8") as f:
+        json.dump({enc_gym(t): r for t, r in cur.items()}, f)
+    gym_ranks = ref_load.data_gym_to_mergeable_bpe_ranks(vocab_bpe, encoder_json)
+    assert gym_ranks == cur and gym_ranks[b"!"] == 0 and len(merges) > 4000
+    e_gym = tiktoken_b200.Encoding("by_data_gym", pat_str=vu.R50K_PAT, mergeable_ranks=gym_ranks, special_tokens={"<|endoftext|>": len(cur)})
+    o2 = _oracle(gym_ranks, {}, vu.R50K_PAT)
+    exp_t, exp_o = o2.encode_ordinary_batch_np(text, off, CORES)
+    assert _same(e_gym.encode_ordinary_packed(text, off), exp_t, exp_o)
