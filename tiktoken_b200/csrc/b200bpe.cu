@@ -683,7 +683,7 @@ static int enqueue_pipeline(b200bpe *h, DevCtx *D, Slot &S, const PipeArgs &a) {
         CUDA_TRY(cudaEventRecord(S.ev[11], ls));
         LongScratch LS{S.w_idA.p, S.w_rkA.p, S.w_idB.p, S.w_rkB.p, S.w_aux1.p, S.w_aux2.p, S.w_flag.p};
         if (h->pmerge) {         // 129..1024 bytes: segmented parallel merge (rounds, not merges, are sequential); shorter: a group of lanes per piece
-            pmerge_kernel<<<148 * 5, PM_WARPS * 32, 0, ls>>>(a.d_text, D->T, q, S.w_ltok.p, S.d_ctr, h->pmerge_min_cls);
+            pmerge_kernel<<<148 * PM_BLOCKS_PER_SM, PM_WARPS * 32, 0, ls>>>(a.d_text, D->T, q, S.w_ltok.p, S.d_ctr, h->pmerge_min_cls);
             pmerge_long_kernel<<<148 * 4, PM_WARPS_L * 32, 0, ls>>>(a.d_text, D->T, q, S.w_ltok.p, S.d_ctr);
             if (h->pmerge_min_cls > 2) mid_group32_kernel<<<148 * 4, MIDG_WARPS * 32, 0, ls>>>(a.d_text, D->T, q, S.w_ltok.p, S.d_ctr, 2);
             if (h->pmerge_min_cls > 0) mid_group16_kernel<<<148 * 9, MIDG_WARPS * 32, 0, ls>>>(a.d_text, D->T, q, S.w_ltok.p, S.d_ctr);

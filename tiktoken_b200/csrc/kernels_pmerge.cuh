@@ -1,6 +1,7 @@
 // kernels_pmerge.cuh -- pieces of 17..256 bytes (CJK runs, indentation, separators, long identifiers): the SEGMENTED
-// PARALLEL MERGE.  A warp packs several pieces of one length class into a 512-part buffer in shared memory and merges
-// them together, a handful of ROUNDS for the whole batch instead of one round per merge and piece.
+// PARALLEL MERGE.  A warp takes a batch of pieces of one length class (one piece of <= 256 or <= 1024 bytes as shipped;
+// the code packs several shorter ones) into a buffer of parts in shared memory and merges them together, a handful of
+// ROUNDS for the whole batch instead of one round per merge and piece.
 //
 // `_byte_pair_merge` (src/lib.rs:140-196) merges ONE pair per step: the smallest rank, leftmost on ties.  If merges
 // never created pairs, that loop would walk the pairs in (rank, position) order and take a pair unless a neighbour was
@@ -246,16 +247,22 @@ __device__ void pmerge_class(const uint8_t *__restrict__ text, const DevTables &
     }
 }
 
-// 129..256 bytes: two pieces per 512-part batch (and, optionally, the shorter classes: 4, 8, 16 pieces per batch)
+// 129..256 bytes: PM_CAP3 / 256 pieces per batch (and, optionally, the shorter classes).  One piece per 256-part buffer
+// (4.9 KiB of shared memory per warp, 40 warps per SM) beats two per 512-part buffer (9.7 KiB, 20 warps): the kernel is
+// bound by latency and L1TEX, not by instruction issue (config 3, 256 MiB: long-piece stage 7.69 -> 6.92 ms).
+#ifndef PM_CAP3
+#define PM_CAP3 256
+#endif
 __global__ void __launch_bounds__(PM_WARPS * 32) pmerge_kernel(const uint8_t *__restrict__ text, DevTables T, LongQ q, uint32_t *ltok,
                                                               Counters *ctr, int min_cls) {
-    __shared__ PMergeSmem<512> smem[PM_WARPS];
-    PMergeSmem<512> &S = smem[threadIdx.x >> 5];
-    pmerge_class<512>(text, T, q, 3, 2, ltok, ctr, S);
-    if (min_cls <= 2) pmerge_class<512>(text, T, q, 2, 4, ltok, ctr, S);
-    if (min_cls <= 1) pmerge_class<512>(text, T, q, 1, 8, ltok, ctr, S);
-    if (min_cls <= 0) pmerge_class<512>(text, T, q, 0, 16, ltok, ctr, S);
+    __shared__ PMergeSmem<PM_CAP3> smem[PM_WARPS];
+    PMergeSmem<PM_CAP3> &S = smem[threadIdx.x >> 5];
+    pmerge_class<PM_CAP3>(text, T, q, 3, PM_CAP3 / 256, ltok, ctr, S);
+    if (min_cls <= 2) pmerge_class<PM_CAP3>(text, T, q, 2, PM_CAP3 / 128, ltok, ctr, S);
+    if (min_cls <= 1) pmerge_class<PM_CAP3>(text, T, q, 1, PM_CAP3 / 64, ltok, ctr, S);
+    if (min_cls <= 0) pmerge_class<PM_CAP3>(text, T, q, 0, PM_CAP3 / 32, ltok, ctr, S);
 }
+static const int PM_BLOCKS_PER_SM = PM_CAP3 == 256 ? 11 : 5;
 
 // 257..1024 bytes: one piece per 1024-part batch
 static const int PM_WARPS_L = 2;
