@@ -474,7 +474,7 @@ extern "C" int b200bpe_create_multi(const uint8_t *tok_bytes, const uint64_t *to
     if (const char *cm = getenv("B200BPE_CHUNK_MB")) { long v = atol(cm); if (v >= 1 && v <= 2048) { h->chunk_bytes = (size_t)v << 20; h->chunk_forced = true; } }
     h->mid_group = H.max_rank < MIDG_MAX_RANK && env_long("B200BPE_MID_GROUP", 1, 0, 1) != 0;
     h->pmerge = h->mid_group && env_long("B200BPE_PMERGE", 1, 0, 1) != 0;
-    h->pmerge_min_cls = (int)env_long("B200BPE_PMERGE_MIN_CLS", 3, 0, 3);
+    h->pmerge_min_cls = (int)env_long("B200BPE_PMERGE_MIN_CLS", 3, 1, 3);
     h->copy_threads = (int)env_long("B200BPE_COPY_THREADS", std::max(1u, std::min(16u, std::thread::hardware_concurrency() / 4)), 1, 64);
     {   // tokens return over PCIe as bit fields just wide enough for the largest id (17 bits for cl100k, 18 for o200k, 16 for
         // r50k / p50k instead of 32): the return traffic shares the link with the text going up
@@ -683,13 +683,15 @@ static int enqueue_pipeline(b200bpe *h, DevCtx *D, Slot &S, const PipeArgs &a) {
         CUDA_TRY(cudaEventRecord(S.ev[11], ls));
         LongScratch LS{S.w_idA.p, S.w_rkA.p, S.w_idB.p, S.w_rkB.p, S.w_aux1.p, S.w_aux2.p, S.w_flag.p};
         if (h->pmerge) {         // 129..1024 bytes: segmented parallel merge (rounds, not merges, are sequential); shorter: a group of lanes per piece
-            pmerge_kernel<<<148 * PM_BLOCKS_PER_SM, PM_WARPS * 32, 0, ls>>>(a.d_text, D->T, q, S.w_ltok.p, S.d_ctr, h->pmerge_min_cls);
+            pmerge_kernel<256, 3><<<148 * 10, PM_WARPS * 32, 0, ls>>>(a.d_text, D->T, q, S.w_ltok.p, S.d_ctr);
             pmerge_long_kernel<<<148 * 4, PM_WARPS_L * 32, 0, ls>>>(a.d_text, D->T, q, S.w_ltok.p, S.d_ctr);
-            if (h->pmerge_min_cls > 2) mid_group32_kernel<<<148 * 4, MIDG_WARPS * 32, 0, ls>>>(a.d_text, D->T, q, S.w_ltok.p, S.d_ctr, 2);
-            if (h->pmerge_min_cls > 0) mid_group16_kernel<<<148 * 9, MIDG_WARPS * 32, 0, ls>>>(a.d_text, D->T, q, S.w_ltok.p, S.d_ctr);
+            if (h->pmerge_min_cls <= 2) pmerge_kernel<128, 2><<<148 * 16, PM_WARPS * 32, 0, ls>>>(a.d_text, D->T, q, S.w_ltok.p, S.d_ctr);
+            else mid_group32_kernel<<<148 * 4, MIDG_WARPS * 32, 0, ls>>>(a.d_text, D->T, q, S.w_ltok.p, S.d_ctr, 2);
+            if (h->pmerge_min_cls <= 1) pmerge_kernel<64, 1><<<148 * 16, PM_WARPS * 32, 0, ls>>>(a.d_text, D->T, q, S.w_ltok.p, S.d_ctr);
+            mid_group16_kernel<<<148 * 9, MIDG_WARPS * 32, 0, ls>>>(a.d_text, D->T, q, S.w_ltok.p, S.d_ctr, h->pmerge_min_cls <= 1 ? 0 : 1);
         } else if (h->mid_group) {      // 17..1024 bytes: a group of lanes per piece, state in shared memory
             mid_group32_kernel<<<148 * 4, MIDG_WARPS * 32, 0, ls>>>(a.d_text, D->T, q, S.w_ltok.p, S.d_ctr, 4);
-            mid_group16_kernel<<<148 * 9, MIDG_WARPS * 32, 0, ls>>>(a.d_text, D->T, q, S.w_ltok.p, S.d_ctr);
+            mid_group16_kernel<<<148 * 9, MIDG_WARPS * 32, 0, ls>>>(a.d_text, D->T, q, S.w_ltok.p, S.d_ctr, 1);
         } else {                 // ranks of 2^22 and above: one piece per lane (72 KiB of columns per block) / warp per piece
             mid_thread_kernel<<<148 * 3, MID_WARPS * 32, MID_SMEM_BYTES, ls>>>(a.d_text, D->T, q, S.w_ltok.p, S.d_ctr);
             long_piece_kernel<<<148 * 8, LONG_WARPS * 32, 0, ls>>>(a.d_text, D->T, q, LS, S.w_ltok.p, S.d_ctr, CLS_G1024);

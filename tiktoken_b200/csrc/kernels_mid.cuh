@@ -238,9 +238,9 @@ __global__ void __launch_bounds__(MIDG_WARPS * 32, 4) mid_group32_kernel(const u
 
 // 16 parts per lane (6 KiB of state per warp): 33..64 and 17..32 bytes
 __global__ void __launch_bounds__(MIDG_WARPS * 32, 9) mid_group16_kernel(const uint8_t *__restrict__ text, DevTables T, LongQ q,
-                                                                        uint32_t *ltok, Counters *ctr) {
+                                                                        uint32_t *ltok, Counters *ctr, int max_cls) {
     __shared__ MidGSmem<16> smem[MIDG_WARPS];
     MidGSmem<16> &S = smem[threadIdx.x >> 5];
-    midg_class<4, 16>(text, T, q, 1, ltok, ctr, S);
+    if (max_cls >= 1) midg_class<4, 16>(text, T, q, 1, ltok, ctr, S);
     midg_class<2, 16>(text, T, q, 0, ltok, ctr, S);
 }

@@ -247,22 +247,16 @@ __device__ void pmerge_class(const uint8_t *__restrict__ text, const DevTables &
     }
 }
 
-// 129..256 bytes: PM_CAP3 / 256 pieces per batch (and, optionally, the shorter classes).  One piece per 256-part buffer
-// (4.9 KiB of shared memory per warp, 40 warps per SM) beats two per 512-part buffer (9.7 KiB, 20 warps): the kernel is
-// bound by latency and L1TEX, not by instruction issue (config 3, 256 MiB: long-piece stage 7.69 -> 6.92 ms).
-#ifndef PM_CAP3
-#define PM_CAP3 256
-#endif
+// One piece per buffer of CAP parts, CAP = the upper length of the class: 129..256 bytes -> 256 parts (4.9 KiB of shared
+// memory per warp, 40 warps per SM), 65..128 -> 128, 33..64 -> 64.  One piece per 256-part buffer beats two per 512-part
+// buffer (9.7 KiB, 20 warps per SM): the kernel is bound by latency and L1TEX, not by instruction issue (config 3, 256 MiB:
+// long-piece stage 7.69 -> 6.92 ms).
+template <int CAP, int CLS>
 __global__ void __launch_bounds__(PM_WARPS * 32) pmerge_kernel(const uint8_t *__restrict__ text, DevTables T, LongQ q, uint32_t *ltok,
-                                                              Counters *ctr, int min_cls) {
-    __shared__ PMergeSmem<PM_CAP3> smem[PM_WARPS];
-    PMergeSmem<PM_CAP3> &S = smem[threadIdx.x >> 5];
-    pmerge_class<PM_CAP3>(text, T, q, 3, PM_CAP3 / 256, ltok, ctr, S);
-    if (min_cls <= 2) pmerge_class<PM_CAP3>(text, T, q, 2, PM_CAP3 / 128, ltok, ctr, S);
-    if (min_cls <= 1) pmerge_class<PM_CAP3>(text, T, q, 1, PM_CAP3 / 64, ltok, ctr, S);
-    if (min_cls <= 0) pmerge_class<PM_CAP3>(text, T, q, 0, PM_CAP3 / 32, ltok, ctr, S);
+                                                              Counters *ctr) {
+    __shared__ PMergeSmem<CAP> smem[PM_WARPS];
+    pmerge_class<CAP>(text, T, q, CLS, 1, ltok, ctr, smem[threadIdx.x >> 5]);
 }
-static const int PM_BLOCKS_PER_SM = PM_CAP3 == 256 ? 11 : 5;
 
 // 257..1024 bytes: one piece per 1024-part batch
 static const int PM_WARPS_L = 2;
