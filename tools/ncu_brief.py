@@ -3,7 +3,7 @@
 import csv, subprocess, sys
 raw = subprocess.run(["ncu", "-i", sys.argv[1], "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(raw.splitlines())); hdr = rows[0]; ix = {h: i for i, h in enumerate(hdr)}
-KEYS = [("dur_us", "gpu__time_duration.sum"), ("inst_M", "smsp__inst_executed.sum"), ("issue%", "smsp__issue_active.avg.pct_of_peak_sustained_active"),
+KEYS = [("dur", "gpu__time_duration.sum"), ("inst_M", "smsp__inst_executed.sum"), ("issue%", "smsp__issue_active.avg.pct_of_peak_sustained_active"),
         ("alu%", "sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active"), ("fmaheavy%", "sm__pipe_fmaheavy_cycles_active.avg.pct_of_peak_sustained_elapsed"),
         ("lsu%", "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active"), ("l1tex%", "l1tex__throughput.avg.pct_of_peak_sustained_active"),
         ("l1wave%", "l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed"), ("l1hit%", "l1tex__t_sector_hit_rate.pct"),
@@ -22,7 +22,8 @@ for r in rows[2:]:
             try: v = float(r[ix[m]])
             except ValueError: continue
             if k == "inst_M": v /= 1e6
-            if k.endswith("_MB") and rows[1][ix[m]] == "byte": v /= 1e6
+            if k == "dur": out.append(f"dur={v:.3f}{rows[1][ix[m]]}"); continue
+            if k.endswith("_MB"): v *= {"byte": 1e-6, "Kbyte": 1e-3, "Mbyte": 1.0, "Gbyte": 1e3}.get(rows[1][ix[m]], 1.0); out.append(f"{k}={v:.1f}"); continue
             out.append(f"{k}={v:.1f}")
     tot = sum(float(r[i]) for i in stall) or 1
     top = sorted(stall, key=lambda i: -float(r[i]))[:5]

@@ -35,8 +35,10 @@ def main(rep, out_prefix):
                 lines.append(f"{w} = {r[ix[w]]} {units[ix[w]]}")
         rd = unit_bytes(r[ix["dram__bytes_read.sum"]], units[ix["dram__bytes_read.sum"]])
         wr = unit_bytes(r[ix["dram__bytes_write.sum"]], units[ix["dram__bytes_write.sum"]])
-        traffic[name.split("<")[0]] = {"dram_bytes_per_launch": rd + wr, "dram_read": rd, "dram_write": wr,
-                                       "duration_ms_under_ncu": float(r[ix["gpu__time_duration.sum"]])}
+        key = name.split("<")[0]                      # template instances share a key: keep the launch that moves the most
+        if key not in traffic or rd + wr > traffic[key]["dram_bytes_per_launch"]:
+            traffic[key] = {"dram_bytes_per_launch": rd + wr, "dram_read": rd, "dram_write": wr,
+                            "duration_under_ncu": float(r[ix["gpu__time_duration.sum"]]), "duration_unit": units[ix["gpu__time_duration.sum"]]}
         src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass",
                               "--kernel-name", "regex:" + name.split("<")[0]], capture_output=True, text=True).stdout
         data, cur = [], None
