@@ -236,7 +236,10 @@ struct Slot {
     }
 };
 
-// Everything that lives on one CUDA device: the replicated tables and three pipeline slots.
+#ifndef B2_N_SLOTS
+#define B2_N_SLOTS 3          // pipeline slots per device: uploads run B2_N_SLOTS - 2 chunks ahead of the kernels
+#endif
+// Everything that lives on one CUDA device: the replicated tables and the pipeline slots.
 struct DevCtx {
     int device = 0;
     uint8_t *arena = nullptr; size_t arena_bytes = 0, hot_bytes = 0;   // all tables in one allocation (one L2 window)
@@ -244,8 +247,8 @@ struct DevCtx {
     uint32_t *d_tok_boff = nullptr; uint8_t *d_tok_blob = nullptr;     // decode: id -> bytes
     SpecialTables sp;                                                  // device copy of the special-token patterns
     uint8_t *d_sp_arena = nullptr;
-    static const int N_SLOTS = 3;
-    Slot slots[3];
+    static const int N_SLOTS = B2_N_SLOTS;
+    Slot slots[B2_N_SLOTS];
     size_t l2_window = 0; float l2_ratio = 0.f;
     int probe_blocks_per_sm = 10;
 };
@@ -1064,11 +1067,13 @@ static void host_worker(HostJob *J, int dev_index, size_t first, size_t step) {
         return B200BPE_OK;
     };
     auto stop = [&]() { return J->error.load() != 0 || J->overflow.load(); };
-    int rc = enqueue_h2d(0);
-    if (rc) return bail(rc);
+    // uploads run AHEAD chunks in front of the kernels; the slot of chunk k + AHEAD last served chunk k + AHEAD - N_SLOTS
+    // <= k - 2, which was drained (its download issued) in an earlier iteration
+    const size_t AHEAD = (size_t)DevCtx::N_SLOTS - 2;
+    int rc = B200BPE_OK;
+    for (size_t k = 0; k < AHEAD && k < mine.size(); k++) { rc = enqueue_h2d(k); if (rc) return bail(rc); }
     for (size_t k = 0; k < mine.size() && !stop(); k++) {
-        // slot (k+1)%3 last served chunk k-2, which was drained in the previous iteration
-        if (k + 1 < mine.size()) { rc = enqueue_h2d(k + 1); if (rc) return bail(rc); }
+        if (k + AHEAD < mine.size()) { rc = enqueue_h2d(k + AHEAD); if (rc) return bail(rc); }
         rc = enqueue_pipeline(h, D, slot_of(k), args_of(k));
         if (rc) return bail(rc);
         if (k >= 1) { rc = drain(k - 1); if (rc) return bail(rc); }   // overlaps with chunk k's kernels
