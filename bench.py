@@ -514,6 +514,17 @@ def main():
                 toks, offs = b.enc.encode_ordinary_batch_to_numpy(docs); dt = time.perf_counter() - t0
                 api["list_str_to_numpy"] = {"value": dbytes / dt / 1e9, "unit": "GB/s", "bytes": dbytes,
                                             "what": "encode_ordinary_batch_to_numpy(list[str]) -> (tokens, offsets) arrays"}
+                # latency of ONE small call (the whole pipeline is ~30 launches + one synchronisation, whatever the size)
+                lat = {}
+                for nbytes_small in (1 << 10, 64 << 10):
+                    small = np.ascontiguousarray(b.text[:nbytes_small]); soff = np.asarray([0, len(small)], np.uint64)
+                    for _ in range(20):
+                        b.enc.encode_ordinary_packed(small, soff).close()
+                    t0 = time.perf_counter()
+                    for _ in range(200):
+                        b.enc.encode_ordinary_packed(small, soff).close()
+                    lat[f"{nbytes_small >> 10}KiB_us"] = (time.perf_counter() - t0) / 200 * 1e6
+                api["small_call_latency"] = dict(lat, what="encode_ordinary_packed of ONE document, host in -> host out, mean of 200 calls")
                 del out, toks, offs, docs, pageable
                 line["api"] = api
             except Exception as e:                                   # noqa: BLE001
