@@ -517,7 +517,8 @@ def main():
                 # latency of ONE small call (the whole pipeline is ~30 launches + one synchronisation, whatever the size)
                 lat = {}
                 for nbytes_small in (1 << 10, 64 << 10):
-                    small = np.ascontiguousarray(b.text[:nbytes_small]); soff = np.asarray([0, len(small)], np.uint64)
+                    cut = int(np.flatnonzero(b.text[:nbytes_small] == 0x20)[-1])      # end the document at a space, not inside a scalar
+                    small = np.ascontiguousarray(b.text[:cut]); soff = np.asarray([0, len(small)], np.uint64)
                     for _ in range(20):
                         b.enc.encode_ordinary_packed(small, soff).close()
                     t0 = time.perf_counter()
