@@ -67,18 +67,11 @@ B2_HD uint32_t b2_mad1(uint32_t v, uint32_t one, uint32_t c) {   // v * one + c 
 // (v * one + c with `one` == 1 at run time, opaque to the compiler -> IMAD); the combining logic and the accumulation
 // (one LEA.HI / SHF+LOP3 per class) stay on the ALU pipe.  A multiply-high accumulate (IMAD.HI) was measured too: it
 // moves more work off the ALU pipe but IMAD.HI issues at a quarter of the IMAD rate (profiles/r02_f_pretok_pipes.txt).
-#ifndef B2_CLASSIFY_FMA
-#define B2_CLASSIFY_FMA 1
-#endif
 template <int K>
 B2_HD void classify_word(uint32_t x, ClassAcc &a, uint32_t one) {
     const uint32_t y = x & 0x7F7F7F7Fu, yl = y | 0x20202020u;
     const uint32_t hi7 = x & 0x80808080u, nx7 = hi7 ^ 0x80808080u;       // bit 7 of every byte: non-ASCII / ASCII
-#if B2_CLASSIFY_FMA
 #define B2_GE(v, n) b2_mad1(v, one, (0x80u - (uint32_t)(n)) * 0x01010101u)  /* bit 7 of every byte: (7-bit v) >= n */
-#else
-#define B2_GE(v, n) ((v) + (0x80u - (uint32_t)(n)) * 0x01010101u)
-#endif
     const uint32_t alpha = B2_GE(yl, 'a') & ~B2_GE(yl, 'z' + 1) & nx7;
     const uint32_t upper = alpha & ~(x << 2);                              // bit 5 clear
     const uint32_t digit = B2_GE(y, '0') & ~B2_GE(y, '9' + 1) & nx7;
