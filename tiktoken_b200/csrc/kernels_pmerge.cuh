@@ -70,7 +70,9 @@ __device__ __forceinline__ uint32_t pm_alt_from_end(uint32_t w, int lane) {
     return __shfl_sync(0xFFFFFFFFu, __brev(x), 31 - lane);
 }
 
-template <int PM_CAP>
+// SINGLE: one piece per batch (as shipped) -- no piece-index array, and the per-piece minima of a round come out of a warp
+// reduction instead of shared-memory atomics (the kernel is bound by shared-memory wavefronts).
+template <int PM_CAP, bool SINGLE>
 __device__ void pmerge_class(const uint8_t *__restrict__ text, const DevTables &T, const LongQ &q, int cls, int per_batch,
                              uint32_t *ltok, Counters *ctr, PMergeSmem<PM_CAP> &S) {
     const int lane = threadIdx.x & 31;
@@ -116,7 +118,7 @@ __device__ void pmerge_class(const uint8_t *__restrict__ text, const DevTables &
                 const uint32_t b = __ldg(piece + j);
                 S.id[bs + j] = __ldg(T.byte_id + b);
                 S.rk[bs + j] = j + 1 < ns ? __ldg(T.pair2 + (b << 8 | __ldg(piece + j + 1))) : PM_SEP;
-                S.seg[bs + j] = (uint8_t)s;
+                if (!SINGLE) S.seg[bs + j] = (uint8_t)s;
             }
         }
         if (lane < 2) S.rk[m + lane] = RANK_MAX;
@@ -129,11 +131,13 @@ __device__ void pmerge_class(const uint8_t *__restrict__ text, const DevTables &
             if (round > PM_CAP) { if (lane == 0) atomicOr(&ctr->err, ERR_INTERNAL); break; }   // every round merges: cannot happen
             const int nw = (int)((m + 31) >> 5);
             // 1. bitmaps: U(e) = key(e-1) < key(e) in (rank, position) order (ones beyond the end), V(e) = mergeable
-            uint32_t myU = 0xFFFFFFFFu, myV = 0;
+            uint32_t myU = 0xFFFFFFFFu, myV = 0, carry = RANK_MAX;       // carry: the rank slot before this iteration's first part
             for (int t = 0; t < nw; t++) {
                 const uint32_t e = 32u * t + lane;
                 const uint32_t r0 = e < m ? rk[e] : RANK_MAX;
-                const uint32_t rm1 = e >= 1 && e < m ? rk[e - 1] : RANK_MAX;
+                const uint32_t up = __shfl_up_sync(0xFFFFFFFFu, r0, 1);    // the left neighbour's slot from its lane, not from shared memory
+                const uint32_t rm1 = lane ? up : carry;
+                carry = __shfl_sync(0xFFFFFFFFu, r0, 31);
                 const uint32_t ub = __ballot_sync(0xFFFFFFFFu, e >= m || (e >= 1 && rm1 <= r0));
                 const uint32_t vb = __ballot_sync(0xFFFFFFFFu, r0 < PM_SEP);
                 if (lane == t) { myU = ub; myV = vb; }
@@ -157,6 +161,7 @@ __device__ void pmerge_class(const uint8_t *__restrict__ text, const DevTables &
             }
             __syncwarp();
             // 3. the two pairs every member's merge creates -- all lanes busy, four table loads in flight per lane
+            uint32_t myT = RANK_MAX, myC1 = RANK_MAX;
             for (uint32_t i = lane; i < n_taken; i += 32) {
                 const uint32_t e = S.list[i];
                 const uint32_t r0 = rk[e];
@@ -178,16 +183,23 @@ __device__ void pmerge_class(const uint8_t *__restrict__ text, const DevTables &
                 else if (has_l) vl = pair_lookup(T, L, r0);
                 else if (has_r) vr = pair_lookup(T, r0, R);
                 S.nl[e] = vl; S.nr[e] = has_r ? vr : PM_SEP;             // no right part: the merged part becomes the last one of its piece
-                const uint32_t s = seg[e];
-                atomicMin(&S.T[s], min(vl, vr));
-                atomicMin(&S.c1[s], (r0 << PM_POS_BITS) | e);
+                if (SINGLE) { myT = min(myT, min(vl, vr)); myC1 = min(myC1, (r0 << PM_POS_BITS) | e); }
+                else {
+                    const uint32_t s = seg[e];
+                    atomicMin(&S.T[s], min(vl, vr));
+                    atomicMin(&S.c1[s], (r0 << PM_POS_BITS) | e);
+                }
             }
+            if (SINGLE) { myT = warp_min_u32(myT); myC1 = warp_min_u32(myC1) & ((1u << PM_POS_BITS) - 1u); }
             __syncwarp();
             // 4a. commit: below every created rank of the piece, or the piece's minimum
             for (int t = 0; t < nw; t++) {
                 const uint32_t e = 32u * t + lane;
                 bool com = (S.tbits[1 + t] >> lane) & 1u;
-                if (com) { const uint32_t s = seg[e]; com = rk[e] < S.T[s] || e == (S.c1[s] & ((1u << PM_POS_BITS) - 1u)); }
+                if (com) {
+                    if (SINGLE) com = rk[e] < myT || e == myC1;
+                    else { const uint32_t s = seg[e]; com = rk[e] < S.T[s] || e == (S.c1[s] & ((1u << PM_POS_BITS) - 1u)); }
+                }
                 const uint32_t cb = __ballot_sync(0xFFFFFFFFu, com);
                 if (lane == 0) S.cbits[1 + t] = cb;
             }
@@ -207,7 +219,7 @@ __device__ void pmerge_class(const uint8_t *__restrict__ text, const DevTables &
                 uint32_t nid = 0, nrk = 0, sg = 0;
                 if (keep) {
                     const uint32_t r0 = rk[e];
-                    sg = seg[e];
+                    if (!SINGLE) sg = seg[e];
                     if (com_e) {                                     // (the pair two places on only counts inside the same piece)
                         nid = r0; nrk = S.nr[e];
                         if (nrk != PM_SEP && com_p2 && r0 <= rk[e + 2]) nrk = S.nl[e + 2];
@@ -217,7 +229,7 @@ __device__ void pmerge_class(const uint8_t *__restrict__ text, const DevTables &
                 __syncwarp();
                 if (keep) {
                     const uint32_t pos = out + __popc(kb & lt_mask);
-                    id[pos] = nid; rk[pos] = nrk; seg[pos] = (uint8_t)sg;
+                    id[pos] = nid; rk[pos] = nrk; if (!SINGLE) seg[pos] = (uint8_t)sg;
                 }
                 out += __popc(kb);
                 __syncwarp();
@@ -228,7 +240,8 @@ __device__ void pmerge_class(const uint8_t *__restrict__ text, const DevTables &
         }
         // ---- tokens: the parts of every piece, left to right ----------------------------------------------------------
         {
-            for (uint32_t e = lane; e < m; e += 32) {
+            if (SINGLE) { if (lane == 0) { S.seg_lo[0] = 0; S.seg_hi[0] = m; } }
+            else for (uint32_t e = lane; e < m; e += 32) {
                 const uint32_t s = seg[e];
                 if (e == 0 || seg[e - 1] != s) S.seg_lo[s] = e;
                 if (e + 1 == m || seg[e + 1] != s) S.seg_hi[s] = e + 1;
@@ -236,7 +249,7 @@ __device__ void pmerge_class(const uint8_t *__restrict__ text, const DevTables &
             __syncwarp();
             bool bad = false;
             for (uint32_t e = lane; e < m; e += 32) {
-                const uint32_t s = seg[e];
+                const uint32_t s = SINGLE ? 0u : (uint32_t)seg[e];
                 const uint32_t x = id[e];
                 ltok[S.pst[s] + (e - S.seg_lo[s])] = x; bad |= x >= PSEUDO_BASE;
             }
@@ -255,7 +268,7 @@ template <int CAP, int CLS>
 __global__ void __launch_bounds__(PM_WARPS * 32) pmerge_kernel(const uint8_t *__restrict__ text, DevTables T, LongQ q, uint32_t *ltok,
                                                               Counters *ctr) {
     __shared__ PMergeSmem<CAP> smem[PM_WARPS];
-    pmerge_class<CAP>(text, T, q, CLS, 1, ltok, ctr, smem[threadIdx.x >> 5]);
+    pmerge_class<CAP, true>(text, T, q, CLS, 1, ltok, ctr, smem[threadIdx.x >> 5]);
 }
 
 // 257..1024 bytes: one piece per 1024-part batch
@@ -264,5 +277,5 @@ __global__ void __launch_bounds__(PM_WARPS_L * 32) pmerge_long_kernel(const uint
                                                                      uint32_t *ltok, Counters *ctr) {
     __shared__ PMergeSmem<1024> smem[PM_WARPS_L];
     PMergeSmem<1024> &S = smem[threadIdx.x >> 5];
-    pmerge_class<1024>(text, T, q, CLS_G1024, 1, ltok, ctr, S);
+    pmerge_class<1024, true>(text, T, q, CLS_G1024, 1, ltok, ctr, S);
 }
