@@ -156,27 +156,32 @@ __device__ void pmerge_class(const uint8_t *__restrict__ text, const DevTables &
                 if (lane < np) { S.T[lane] = RANK_MAX; S.c1[lane] = RANK_MAX; }
                 const uint32_t c = __popc(tk), inc = warp_incl_scan_u32(c, lane);
                 n_taken = __shfl_sync(0xFFFFFFFFu, inc, 31);
+                // a list entry = position (10 bits) | "the pair two places to the left / right is a member too" (bits 10, 11):
+                // the probes then need no look-ups in the bitmap
+                const uint32_t prevw = __shfl_up_sync(0xFFFFFFFFu, tk, 1), nextw = __shfl_down_sync(0xFFFFFFFFu, tk, 1);
+                const uint32_t tm2 = (tk << 2) | (lane ? prevw >> 30 : 0u), tp2 = (tk >> 2) | (lane < 31 ? nextw << 30 : 0u);
                 uint16_t *dst = S.list + (inc - c);
-                for (uint32_t mm = tk; mm; mm &= mm - 1) *dst++ = (uint16_t)(32 * lane + __ffs(mm) - 1);
+                for (uint32_t mm = tk; mm; mm &= mm - 1) {
+                    const int j = __ffs(mm) - 1;
+                    *dst++ = (uint16_t)((32 * lane + j) | (((tm2 >> j) & 1u) << 10) | (((tp2 >> j) & 1u) << 11));
+                }
             }
             __syncwarp();
             // 3. the two pairs every member's merge creates -- all lanes busy, four table loads in flight per lane
             uint32_t myT = RANK_MAX, myC1 = RANK_MAX;
             for (uint32_t i = lane; i < n_taken; i += 32) {
-                const uint32_t e = S.list[i];
+                const uint32_t ent = S.list[i], e = ent & 1023u;
                 const uint32_t r0 = rk[e];
                 const bool has_l = e >= 1 && rk[e - 1] != PM_SEP;        // a part of the same piece to the left
                 const bool has_r = rk[e + 1] != PM_SEP;                  // ... after the pair, to the right
                 uint32_t L = 0, R = 0;
                 if (has_l) {
                     const uint32_t r2 = e >= 2 ? rk[e - 2] : RANK_MAX;
-                    const bool tk2 = e >= 2 && ((S.tbits[1 + ((e - 2) >> 5)] >> ((e - 2) & 31)) & 1u);
-                    L = tk2 && r2 <= r0 ? r2 : id[e - 1];
+                    L = ((ent >> 10) & 1u) && r2 <= r0 ? r2 : id[e - 1];
                 }
                 if (has_r) {
                     const uint32_t r2 = rk[e + 2];
-                    const bool tk2 = (S.tbits[1 + ((e + 2) >> 5)] >> ((e + 2) & 31)) & 1u;
-                    R = tk2 && r2 < r0 ? r2 : id[e + 2];
+                    R = ((ent >> 11) & 1u) && r2 < r0 ? r2 : id[e + 2];
                 }
                 uint32_t vl = RANK_MAX, vr = RANK_MAX;
                 if (has_l && has_r) pair_lookup2(T, L, r0, r0, R, vl, vr);
