@@ -81,7 +81,7 @@ class ClockSampler:
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
-                 "-lms", "20"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                 "-lms", "10"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
         except Exception:
@@ -89,15 +89,25 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append(line.strip())
+            self.rows.append((time.perf_counter(), line.strip()))
 
-    def stop(self):
+    def stop(self, t0=None, t1=None, t_warm=None):
+        """Clocks from the samples that arrived inside [t0, t1] (the timed region).  The sampler is started before the
+        warm-up steps so that it is already running; when fewer than three samples fall inside the timed region (five
+        6.7 ms steps are one or two 10 ms sampling periods) the window is widened to the identical warm-up steps that
+        run back to back before it (from t_warm) and the line says so."""
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        time.sleep(0.05)
         self.proc.terminate()
+        window = "all"
+        rows = self.rows
+        if t0 is not None:
+            rows, window = [r for r in self.rows if t0 <= r[0] <= t1 + 0.02], "timed region"
+            if len(rows) < 3 and t_warm is not None:
+                rows, window = [r for r in self.rows if t_warm <= r[0] <= t1 + 0.02], "warm-up steps + timed region (back to back)"
         sm, mx, reasons = [], None, set()
-        for r in self.rows:
+        for _, r in rows:
             f = [x.strip() for x in r.split(",")]
             if len(f) < 6:
                 continue
@@ -109,7 +119,7 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
-                "samples": len(sm)}
+                "samples": len(sm), "window": window}
 
 
 def load_reference_engine(pat, ranks, special):
@@ -392,15 +402,24 @@ def main():
         if not allok(ok):
             return {"parity": False, "error": "PARITY FAILURE against the oracle"}
         xchg = CountExchange(rank, world, device="cuda")
-        for _ in range(warmup):
-            timed_device_loop(b, 1, world, xchg)                # also warms the NCCL communicator and settles work-space sizes
         sampler = ClockSampler(local_rank) if (sample_clocks and rank == 0) else None
-        barrier()
         if sampler:
-            sampler.start()
-        ms_total, n_tok, placements = timed_device_loop(b, steps, world, xchg)
+            sampler.start()                                     # nvidia-smi needs a moment to come up: start it before the warm-up
+        timed_device_loop(b, 1, world, xchg)                    # also warms the NCCL communicator and settles work-space sizes
+        if sampler:
+            for _ in range(100):                                # ... and wait (bounded) until it delivers
+                if sampler.rows:
+                    break
+                time.sleep(0.02)
+        t_warm = time.perf_counter()
+        for _ in range(max(warmup - 1, 2)):
+            timed_device_loop(b, 1, world, xchg)
         barrier()
-        clocks = sampler.stop() if sampler else None
+        t0 = time.perf_counter()
+        ms_total, n_tok, placements = timed_device_loop(b, steps, world, xchg)
+        t1 = time.perf_counter()
+        barrier()
+        clocks = sampler.stop(t0, t1, t_warm) if sampler else None
         per_rank = [ms_total / steps]
         if world > 1:                                           # which rank set the pace (the MAX is what counts)
             t = torch.tensor([ms_total / steps], dtype=torch.float64, device="cuda")
