@@ -309,7 +309,7 @@ __global__ void __launch_bounds__(MISS_WARPS * 32, MISS_MIN_BLOCKS) miss_kernel(
         const uint32_t mask = merge_short_conv(
             T, [&](int j) { return (bw[(j >> 2) * 32] >> (8 * (j & 3))) & 0xFFu; }, len, n_max, 0xFFFFFFFFu, id, rk);
         if (have) {
-            // the result record the gather reads: count + the first three tokens (97 % of the missed pieces end as <= 3
+            // the result record the gather reads: count + the first three tokens (94 % of the missed pieces end as <= 3
             // tokens); longer results also go to mres.  One 16-byte store per piece instead of a token array + a count.
             const uint32_t c = (uint32_t)__popc(mask);
             uint32_t t[3] = {0, 0, 0}, k = 0; bool bad = false;
