@@ -10,8 +10,70 @@
 #include <Python.h>
 #include <stdint.h>
 #include <string.h>
+#include <unistd.h>
 
-/* pack(seq_of_str) -> (blob: bytes, offsets: bytes holding uint64[n+1]) */
+/* ---- pack(seq_of_str) -> (blob: bytes, offsets: bytes holding uint64[n+1]) ------------------------------------------
+ * The strings are encoded to UTF-8 straight from CPython's compact representation (1 / 2 / 4 bytes per code point)
+ * into their place of ONE blob, by a few threads: the calling thread collects (kind, data, length) of every string under
+ * the GIL, the workers only READ those immutable buffers (no Python API off the calling thread; the list keeps the
+ * strings alive, the caller waits).  ASCII strings are a memcpy.  str.encode semantics: a lone surrogate raises
+ * UnicodeEncodeError (raised by CPython's own encoder on that item, so the exception is the canonical one).
+ * (Round 1 went through PyUnicode_AsUTF8AndSize -- CPython's one-thread encoder plus a cached copy per string -- and
+ * a second memcpy: 1.1 GB/s, as slow as the whole GPU path is fast.) */
+#include <pthread.h>
+
+typedef struct { const void *data; Py_ssize_t len; int kind; int ascii; } StrView;
+typedef struct {
+    const StrView *v; uint64_t *size_or_off; char *dst; Py_ssize_t lo, hi; Py_ssize_t bad;   /* bad: first item with a lone surrogate */
+    int phase;
+} PackJob;
+
+#define UTF8_SIZE_LOOP(T)                                                                                        \
+    { const T *p = (const T *)s->data; uint32_t sur = 0;                                                           \
+      for (Py_ssize_t i = 0; i < s->len; i++) { const uint32_t c = p[i];                                            \
+          n += 1u + (c >= 0x80u) + (c >= 0x800u) + (c >= 0x10000u); sur |= (uint32_t)(c - 0xD800u < 0x800u); }      \
+      if (sur) *surrogate = 1; }
+#define UTF8_WRITE_LOOP(T)                                                                                       \
+    { const T *p = (const T *)s->data;                                                                             \
+      for (Py_ssize_t i = 0; i < s->len; i++) { const uint32_t c = p[i];                                            \
+          if (c < 0x80u) *d++ = (uint8_t)c;                                                                         \
+          else if (c < 0x800u) { *d++ = (uint8_t)(0xC0 | (c >> 6)); *d++ = (uint8_t)(0x80 | (c & 0x3F)); }          \
+          else if (c < 0x10000u) { *d++ = (uint8_t)(0xE0 | (c >> 12)); *d++ = (uint8_t)(0x80 | ((c >> 6) & 0x3F)); *d++ = (uint8_t)(0x80 | (c & 0x3F)); } \
+          else { *d++ = (uint8_t)(0xF0 | (c >> 18)); *d++ = (uint8_t)(0x80 | ((c >> 12) & 0x3F)); *d++ = (uint8_t)(0x80 | ((c >> 6) & 0x3F)); *d++ = (uint8_t)(0x80 | (c & 0x3F)); } } }
+static uint64_t utf8_size(const StrView *s, int *surrogate) {
+    if (s->ascii) return (uint64_t)s->len;
+    uint64_t n = 0;
+    if (s->kind == 1) { const uint8_t *p = (const uint8_t *)s->data; for (Py_ssize_t i = 0; i < s->len; i++) n += 1u + (p[i] >> 7); }
+    else if (s->kind == 2) UTF8_SIZE_LOOP(uint16_t)
+    else UTF8_SIZE_LOOP(uint32_t)
+    return n;
+}
+static void utf8_write(const StrView *s, uint8_t *d) {
+    if (s->ascii) { memcpy(d, s->data, (size_t)s->len); return; }
+    if (s->kind == 1) UTF8_WRITE_LOOP(uint8_t)
+    else if (s->kind == 2) UTF8_WRITE_LOOP(uint16_t)
+    else UTF8_WRITE_LOOP(uint32_t)
+}
+static void *pack_worker(void *arg) {
+    PackJob *j = (PackJob *)arg;
+    for (Py_ssize_t i = j->lo; i < j->hi; i++) {
+        if (j->phase == 0) {
+            int sur = 0;
+            j->size_or_off[i] = utf8_size(&j->v[i], &sur);
+            if (sur && j->bad < 0) j->bad = i;
+        } else utf8_write(&j->v[i], (uint8_t *)j->dst + j->size_or_off[i]);
+    }
+    return NULL;
+}
+/* items [0, n) split into runs of about equal CODE POINT counts, one run per thread */
+static void pack_run(PackJob *jobs, int nt, int phase) {
+    pthread_t th[64];
+    for (int t = 0; t < nt; t++) jobs[t].phase = phase;
+    for (int t = 1; t < nt; t++) if (pthread_create(&th[t], NULL, pack_worker, &jobs[t]) != 0) { pack_worker(&jobs[t]); th[t] = 0; }
+    pack_worker(&jobs[0]);
+    for (int t = 1; t < nt; t++) if (th[t]) pthread_join(th[t], NULL);
+}
+
 static PyObject *pack(PyObject *self, PyObject *arg) {
     (void)self;
     PyObject *seq = PySequence_Fast(arg, "expected a sequence of str");
@@ -19,31 +81,55 @@ static PyObject *pack(PyObject *self, PyObject *arg) {
     const Py_ssize_t n = PySequence_Fast_GET_SIZE(seq);
     PyObject **items = PySequence_Fast_ITEMS(seq);
     PyObject *offs = PyBytes_FromStringAndSize(NULL, (Py_ssize_t)((n + 1) * sizeof(uint64_t)));
-    if (!offs) { Py_DECREF(seq); return NULL; }
+    StrView *v = (StrView *)PyMem_Malloc((size_t)(n + 1) * sizeof(StrView));
+    PyObject *blob = NULL;
+    if (!offs || !v) { PyErr_NoMemory(); goto fail; }
     uint64_t *off = (uint64_t *)PyBytes_AS_STRING(offs);
-    uint64_t total = 0;
+    uint64_t total_cp = 0;
     for (Py_ssize_t i = 0; i < n; i++) {
-        Py_ssize_t len;
-        if (!PyUnicode_Check(items[i])) {
-            PyErr_SetString(PyExc_TypeError, "expected str");
-            Py_DECREF(offs); Py_DECREF(seq); return NULL;
+        if (!PyUnicode_Check(items[i])) { PyErr_SetString(PyExc_TypeError, "expected str"); goto fail; }
+        v[i].data = PyUnicode_DATA(items[i]); v[i].len = PyUnicode_GET_LENGTH(items[i]);
+        v[i].kind = (int)PyUnicode_KIND(items[i]); v[i].ascii = PyUnicode_IS_ASCII(items[i]) ? 1 : 0;
+        total_cp += (uint64_t)v[i].len;
+    }
+    {
+        long ncpu = sysconf(_SC_NPROCESSORS_ONLN);
+        int nt = (int)(total_cp >> 20);                            /* one thread per MiB of code points ... */
+        if (nt > 16) nt = 16;
+        if (ncpu > 0 && nt > ncpu) nt = (int)ncpu;                 /* ... up to 16 / the machine */
+        if (nt < 1) nt = 1;
+        PackJob jobs[64];
+        Py_ssize_t lo = 0; uint64_t acc = 0;
+        for (int t = 0; t < nt; t++) {
+            const uint64_t want = total_cp / (uint64_t)nt * (uint64_t)(t + 1);
+            Py_ssize_t hi = lo;
+            if (t == nt - 1) hi = n; else while (hi < n && acc + (uint64_t)v[hi].len <= want) acc += (uint64_t)v[hi++].len;
+            jobs[t].v = v; jobs[t].size_or_off = off; jobs[t].dst = NULL; jobs[t].lo = lo; jobs[t].hi = hi; jobs[t].bad = -1;
+            lo = hi;
         }
-        /* raises UnicodeEncodeError on lone surrogates, like str.encode("utf-8") */
-        if (!PyUnicode_AsUTF8AndSize(items[i], &len)) { Py_DECREF(offs); Py_DECREF(seq); return NULL; }
-        off[i] = total;
-        total += (uint64_t)len;
+        pack_run(jobs, nt, 0);                                     /* sizes */
+        Py_ssize_t bad = -1;
+        for (int t = 0; t < nt; t++) if (jobs[t].bad >= 0 && (bad < 0 || jobs[t].bad < bad)) bad = jobs[t].bad;
+        if (bad >= 0) {                                            /* the canonical UnicodeEncodeError of that string */
+            Py_ssize_t len;
+            if (PyUnicode_AsUTF8AndSize(items[bad], &len)) PyErr_SetString(PyExc_UnicodeEncodeError, "surrogates not allowed");
+            goto fail;
+        }
+        uint64_t total = 0;
+        for (Py_ssize_t i = 0; i < n; i++) { const uint64_t sz = off[i]; off[i] = total; total += sz; }
+        off[n] = total;
+        blob = PyBytes_FromStringAndSize(NULL, (Py_ssize_t)total);
+        if (!blob) goto fail;
+        for (int t = 0; t < nt; t++) jobs[t].dst = PyBytes_AS_STRING(blob);
+        pack_run(jobs, nt, 1);                                     /* bytes */
     }
-    off[n] = total;
-    PyObject *blob = PyBytes_FromStringAndSize(NULL, (Py_ssize_t)total);
-    if (!blob) { Py_DECREF(offs); Py_DECREF(seq); return NULL; }
-    char *dst = PyBytes_AS_STRING(blob);
-    for (Py_ssize_t i = 0; i < n; i++) {
-        Py_ssize_t len;
-        const char *src = PyUnicode_AsUTF8AndSize(items[i], &len);   /* cached by the first pass */
-        memcpy(dst + off[i], src, (size_t)len);
-    }
+    PyMem_Free(v);
     Py_DECREF(seq);
     return Py_BuildValue("(NN)", blob, offs);
+fail:
+    PyMem_Free(v);
+    Py_XDECREF(offs); Py_DECREF(seq);
+    return NULL;
 }
 
 /* unpack(tokens_addr: int, offsets_addr: int, n_docs: int) -> list[list[int]] */
