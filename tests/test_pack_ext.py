@@ -52,3 +52,21 @@ def test_pack_errors():
         _b200pack.pack(["a", 5])
     with pytest.raises(TypeError):
         _b200pack.pack(["a", b"bytes"])
+
+
+def test_unpack_shares_the_int_objects_of_the_cache():
+    """`unpack`: token arrays -> list[list[int]]; ids inside the cache come out as the cache's own int objects (no allocation
+    per token), ids beyond it as fresh ints; the lists equal the array slices either way."""
+    rng = np.random.default_rng(5)
+    tok = rng.integers(0, 5000, size=20_000, dtype=np.uint32)
+    tok[::97] = rng.integers(1 << 20, 1 << 31, size=len(tok[::97]), dtype=np.uint32)        # ids beyond the cache
+    off = np.sort(np.concatenate([[0, len(tok), 7, 7], rng.integers(0, len(tok), size=40)])).astype(np.uint64)   # incl. an empty doc
+    cache = list(range(5000))
+    for c in (None, cache):
+        args = (tok.ctypes.data, off.ctypes.data, len(off) - 1) + ((c,) if c is not None else ())
+        out = _b200pack.unpack(*args)
+        assert out == [tok[int(off[i]):int(off[i + 1])].tolist() for i in range(len(off) - 1)]
+    first = next(d for d in out if d)
+    assert all(x is cache[x] for x in first if x < 5000)
+    with pytest.raises(TypeError):
+        _b200pack.unpack(tok.ctypes.data, off.ctypes.data, 2, (1, 2, 3))

@@ -147,6 +147,8 @@ class CoreBPE:
         self.device = int(devs[0])
         self.devices = [int(d) for d in devs]
         self._special = special_tokens
+        self._n_ids = max(int(ranks.max()) + 1 if n_tok else 0, max(special_tokens.values(), default=-1) + 1)   # ids are < this
+        self._int_cache = None
         self._decoder = None
         self._flat = None
         self._lock = threading.Lock()
@@ -204,10 +206,12 @@ class CoreBPE:
         enc = [t.encode("utf-8") for t in texts]
         return _flatten_bytes(enc)
 
-    @staticmethod
-    def _unpack(buf: TokenBuffer) -> list[list[int]]:
+    def _unpack(self, buf: TokenBuffer) -> list[list[int]]:
         if _b200pack is not None and buf.n_tokens:
-            out = _b200pack.unpack(buf.tokens().ctypes.data, buf.offsets().ctypes.data, buf.n_docs)
+            cache = self._int_cache
+            if cache is None:                     # the int objects of all token ids, shared by every list this engine returns
+                cache = self._int_cache = list(range(min(int(self._n_ids), 1 << 20)))
+            out = _b200pack.unpack(buf.tokens().ctypes.data, buf.offsets().ctypes.data, buf.n_docs, cache)
             buf.close()
             return out
         toks = buf.tokens().tolist()
