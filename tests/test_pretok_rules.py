@@ -375,3 +375,29 @@ def test_o200k_prefix_and_apostrophe_rules_are_exact(hostcheck):
     r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "fuzz_cpu.py"), "6", "777"], capture_output=True,
                        text=True, timeout=300, env=dict(os.environ, B200BPE_HOSTCHECK=so))
     assert r.returncode == 0 and "all equal" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+@pytest.mark.parametrize("name", ["cl100k", "o200k"])
+def test_long_whitespace_runs_behind_line_ends(hostcheck, name):
+    """The listed positions behind CR/LF walk their whitespace run eight bytes at a time (ws_run_ahead: SWAR on an aligned
+    64-bit word + the doc-start bits): runs of every length and alignment, with later line ends or none, non-ASCII
+    whitespace inside, ending at a letter, at the document end or at a document boundary in the middle of a run."""
+    pid, pat = PATS[name]
+    o = Oracle(BYTES, {}, pat)
+    rnd = random.Random(2026)
+    ws_ascii = [" ", " ", " ", "\t", "\x0b", "\x0c"]
+    for trial in range(400):
+        parts = []
+        for _ in range(rnd.randint(1, 4)):
+            run = [rnd.choice(ws_ascii) for _ in range(rnd.choice([0, 1, 2, 7, 8, 9, 15, 16, 17, 40, 200]))]
+            for _ in range(rnd.choice([0, 0, 1, 3])):
+                run.insert(rnd.randint(0, len(run)), rnd.choice(["\n", "\r", "\r\n", " ", "　", " "]))
+            parts.append(rnd.choice(["x", "", "é", "1", ".", "\n", "ab\n", "\r"]) + "".join(run) + rnd.choice(["y", "", "\n", "z9", "中"]))
+        text = ("q" * rnd.randint(0, 9)) + "".join(parts)                      # every alignment of the run to the 8-byte words
+        raw = text.encode()
+        cuts = sorted({0, len(raw)} | {rnd.randint(0, len(raw)) for _ in range(rnd.choice([0, 1, 3]))})
+        cuts = [c for c in cuts if c == len(raw) or (raw[c] & 0xC0) != 0x80]   # document boundaries on scalar starts
+        docs = [raw[a:b] for a, b in zip(cuts[:-1], cuts[1:])] or [raw]
+        got, off, _ = fast_starts(hostcheck, pid, docs)
+        for i, d in enumerate(docs):
+            assert np.array_equal(got[int(off[i]):int(off[i + 1])], expected_starts(o, d)), (name, d)
